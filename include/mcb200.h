@@ -1,0 +1,186 @@
+/*
+ * mcb200.h -- C ABI of the B200-native particle-tracking path (libmcb200.so).
+ *
+ * Drop-in boundary for mc-mpi's `Layer` hot path.  Plain C: pointers, sizes,
+ * PODs; no C++ / torch types.  Every entry point names the reference
+ * interface it stands in for (file:line in lkskstlr/mc-mpi).  All functions
+ * return MCB200_OK (0) or a negative error code and never call exit();
+ * mcb200_last_error() gives the message (thread-local).  The reference's own
+ * convention (print + exit, include/gpu_errcheck/gpu_errcheck.hpp:10-18,
+ * src/layer.cpp:276-277) is re-created one level up, in the `cusimulate`
+ * shim and the C++ `Layer` facade (include/mcb200/layer.hpp).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with MCB200_ERR_CUDA.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB200_ABI_VERSION 1
+
+enum {
+  MCB200_OK = 0,
+  MCB200_ERR_INVALID = -1,  /* bad argument / descriptor */
+  MCB200_ERR_CUDA = -2,     /* CUDA runtime error (message has the string) */
+  MCB200_ERR_NOMEM = -3,    /* host or device allocation failed */
+  MCB200_ERR_CAPACITY = -4, /* caller buffer too small */
+  MCB200_ERR_RANGE = -5     /* particle weight above the layer's wmc_max */
+};
+
+/* include/types/particle.hpp:7-18 -- the 24-byte POD the workers ship over
+ * MPI (offsets 0/8/12/16/20).  Same layout, so a `Particle*` can be passed. */
+typedef struct mcb200_particle {
+  uint64_t seed; /* seed_t: state of the particle's own LCG stream */
+  float x;       /* absolute position */
+  float mu;      /* direction cosine */
+  float wmc;     /* Monte-Carlo weight */
+  int32_t index; /* GLOBAL cell index */
+} mcb200_particle;
+
+/* Construction parameters of one layer (= one contiguous sub-slab on one
+ * GPU).  Mirrors Layer::Layer, src/layer.cpp:44-69, plus what the reference
+ * hard-codes (cross-sections) or cannot express (device, tally resolution). */
+typedef struct mcb200_layer_desc {
+  int32_t abi_version;        /* MCB200_ABI_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  float x_min, x_max;         /* sub-slab bounds (layer.hpp:85) */
+  int32_t index_start;        /* first global cell of the sub-slab (layer.hpp:89) */
+  int32_t m;                  /* number of cells (layer.hpp:88) */
+  float dx;                   /* cell width used for edges; <= 0 -> (x_max-x_min)/m
+                                 like layer.cpp:47.  Multi-GPU runs pass the ONE
+                                 global dx so that N GPUs == 1 GPU bit for bit. */
+  float particle_min_weight;  /* layer.hpp:105 */
+  int32_t left_border;        /* 1/0, or -1 -> |x_min| < 1e-4      (layer.cpp:47) */
+  int32_t right_border;       /* 1/0, or -1 -> |x_max - 1| < 1e-4  (layer.cpp:48) */
+  const float *sigs;              /* m floats, or NULL -> expf(-x_mid) (layer.cpp:53-60) */
+  const float *absorption_rates;  /* m floats, or NULL -> 0.5       (layer.cpp:63) */
+  float wmc_max;              /* upper bound of any particle weight this layer
+                                 will ever see (1/nb_particles for a reference
+                                 run).  Sets the fixed-point tally unit:
+                                 2^-k with wmc_max * 2^k in [2^29, 2^30). */
+  int32_t keep_border;        /* 1: particles absorbed at a global border are
+                                 ALSO written to the outboxes (tests); 0: only
+                                 counted, like layer.cpp:350-360 */
+} mcb200_layer_desc;
+
+typedef struct mcb200_layer mcb200_layer;
+
+/* Cumulative counters of a layer (all 64-bit: SURVEY hard part 7). */
+typedef struct mcb200_counts {
+  int64_t nb_disabled;  /* Layer::nb_disabled (layer.hpp:97): dead + absorbed at borders */
+  int64_t nb_active;    /* Layer::nb_active() (layer.cpp:84-87): bank + unborn */
+  int64_t n_bank;       /* particles resident in the device bank */
+  int64_t n_unborn;     /* Layer::nb_particles_create (layer.hpp:109) */
+  int64_t n_outbox_left;   /* = particles_left.size()  (layer.hpp:94) */
+  int64_t n_outbox_right;  /* = particles_right.size() (layer.hpp:95) */
+  int64_t events;       /* particle_step executions (layer.cpp:123) */
+  int64_t scatters;     /* events that took the di < di_edge branch (layer.cpp:160) */
+  int64_t n_left;       /* histories classified -1 (layer.cpp:202-205,217) */
+  int64_t n_right;      /* histories classified +1 (layer.cpp:207-210) */
+  int64_t n_dead;       /* histories classified 0  (layer.cpp:212-215) */
+  double w_left;        /* weight carried out to the left / right / by dead */
+  double w_right;
+  double w_dead;
+  int64_t launches;     /* tracking-kernel launches so far */
+  double track_ms;      /* summed device time of those launches (CUDA events) */
+  int64_t gpu_launches; /* ALL kernels this layer launched (tracking, birth, transposes) */
+} mcb200_counts;
+
+/* ---- life cycle ------------------------------------------------------- */
+/* Layer::Layer, src/layer.cpp:44-69 */
+int mcb200_layer_create(const mcb200_layer_desc *desc, mcb200_layer **out);
+void mcb200_layer_destroy(mcb200_layer *l);
+/* deep copy (Layer is copy-constructed / returned by value in the reference:
+ * src/layer.cpp:41, include/mcmpi/worker.hpp:60) */
+int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out);
+/* overwrite the public, mutable `sigs` / `absorption_rates` vectors
+ * (include/layer/layer.hpp:103-104); either pointer may be NULL = keep */
+int mcb200_layer_set_cross_sections(mcb200_layer *l, const float *sigs,
+                                    const float *absorption_rates);
+int mcb200_layer_get_cross_sections(mcb200_layer *l, float *sigs_out,
+                                    float *absorption_rates_out);
+
+/* ---- particle sources ------------------------------------------------- */
+/* Layer::create_particles(x_ini, wmc, n, seed), src/layer.cpp:71-82: registers
+ * n unborn particles; they are born ON THE DEVICE (rnd_seed chain via LCG
+ * jump-ahead, first rnd_real draw -> mu, src/layer.cpp:101-120) when
+ * simulate() needs them.  No-op when x_ini is outside (x_min, x_max). */
+int mcb200_layer_create_particles(mcb200_layer *l, float x_ini, float wmc,
+                                  int64_t n, uint64_t seed);
+/* append n host particles to the bank -- what the workers do on receive
+ * (src/worker_sync.cpp:47-108, src/async_comm.cpp:140-143, src/rma_comm.cpp:210) */
+int mcb200_layer_push(mcb200_layer *l, const mcb200_particle *aos, int64_t n);
+/* same, from DEVICE memory on the layer's GPU (24-byte records) */
+int mcb200_layer_push_device(mcb200_layer *l, const void *dev_aos, int64_t n);
+
+/* ---- the hot path ----------------------------------------------------- */
+/* Layer::simulate(nb_particles), src/layer.cpp:239-361: tracks the last
+ * `nb_particles` of the bank (births included) until each has left the
+ * sub-slab or dropped below particle_min_weight; -1 = until nothing is left
+ * (simulate_helper, :220-237).  Blocking.  `counts` may be NULL. */
+int mcb200_layer_simulate(mcb200_layer *l, int64_t nb_particles,
+                          mcb200_counts *counts);
+
+/* ---- results ---------------------------------------------------------- */
+int mcb200_layer_counts(mcb200_layer *l, mcb200_counts *out);
+/* particles_left / particles_right (layer.hpp:94-95): copy up to `cap`
+ * escapees to the host and clear the outbox (what the workers do after
+ * sending: worker_sync.cpp:63,75).  Order within an outbox is unspecified. */
+int mcb200_layer_pop_left(mcb200_layer *l, mcb200_particle *aos, int64_t cap,
+                          int64_t *n_out);
+int mcb200_layer_pop_right(mcb200_layer *l, mcb200_particle *aos, int64_t cap,
+                           int64_t *n_out);
+/* same, into DEVICE memory on the layer's GPU (24-byte records) -- the
+ * buffer a neighbour exchange (NCCL send / P2P copy) ships */
+int mcb200_layer_pop_left_device(mcb200_layer *l, void *dev_aos, int64_t cap,
+                                 int64_t *n_out);
+int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap,
+                                  int64_t *n_out);
+/* weights_absorbed (layer.hpp:92), m entries.  _f32 is what the reference
+ * exposes; _f64 and _q are the same tally without the float rounding:
+ * tally = q * 2^-log2_scale exactly. */
+int mcb200_layer_weights_absorbed(mcb200_layer *l, float *out_m);
+int mcb200_layer_weights_absorbed_f64(mcb200_layer *l, double *out_m);
+int mcb200_layer_weights_absorbed_q(mcb200_layer *l, int64_t *out_m,
+                                    int32_t *log2_scale);
+/* Layer::dump_WA(), src/layer.cpp:363-380, same "%.4e %.3e\n" text; path NULL
+ * -> "WA.out" in the current directory like the reference */
+int mcb200_layer_dump_WA(mcb200_layer *l, const char *path);
+
+/* ---- plumbing --------------------------------------------------------- */
+/* the cudaStream_t all of this layer's work is queued on (for CUDA-event
+ * timing by the caller) */
+void *mcb200_layer_stream(mcb200_layer *l);
+/* tuning knobs; key/value, returns MCB200_ERR_INVALID for unknown keys:
+ *   "tally_mode"   0 auto, 1 shared-memory tally, 2 global (L2) tally
+ *   "warp_agg"     0/1 warp-aggregated tally atomics (match.any + redux)
+ *   "block"        threads per CTA,  "blocks_per_sm" CTAs per SM
+ *   "birth_chunk"  max particles born per launch */
+int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value);
+
+const char *mcb200_last_error(void);
+int mcb200_abi_version(void);
+int mcb200_device_count(void);
+
+/* ---- primitives exposed for known-answer tests ------------------------- */
+/* rnd_real on the device, one draw per element: seeds[i] advanced in place,
+ * out[i] = the float (src/curandom.cu:7-14, checked like src/test_curandom.cu) */
+int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host,
+                         int64_t n);
+/* device logf / expf as used by the tracking kernel, element-wise */
+int mcb200_test_logf(int device, const float *in_host, float *out_host, int64_t n);
+int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t n);
+/* device-side birth only: first n particles of create_particles(x_ini,wmc,.,seed) */
+int mcb200_test_birth(int device, float x_ini, float wmc, float dx, int64_t n,
+                      uint64_t seed, mcb200_particle *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

@@ -1,0 +1,443 @@
+// mcb_kernels.cu -- hand-written sm_100a kernels of the particle-tracking path.
+//
+// track_kernel<SHARED, AGG> is the product: a persistent, history-based
+// tracking kernel.  Each lane owns one particle in registers and runs the
+// reference's event loop (src/layer.cpp:123-218) until the particle leaves the
+// sub-slab or drops below particle_min_weight; finished lanes are retired and
+// refilled from the bank inside the loop, so a warp keeps 32 live histories
+// regardless of how unequal their lengths are (293 vs 708 events on the
+// default slab).  Per event:
+//    * 1-2 steps of the per-particle 64-bit LCG (registers only),
+//    * glibc-exact logf / expf in FP64, two IEEE fp32 divides,
+//    * one fixed-point deposit into the CTA-private per-cell tally in shared
+//      memory (native 32-bit ATOMS.ADD + rare carry; optionally aggregated per
+//      warp with match.any + redux), flushed ONCE per CTA with 64-bit REDs,
+//    * escapees compacted with ballot/popc prefix sums into contiguous
+//      left / right outboxes (one global atomic per warp per retire event).
+// Nothing on this path is a contraction: no tensor cores by design.
+#include "mcb_kernels.cuh"
+
+namespace mcb {
+
+#define MCB_FULL 0xffffffffu
+
+// ---------------------------------------------------------------- helpers --
+
+// sum of a signed 32-bit value over the lanes of `mask`, exact in 64 bits.
+// Two 16-bit halves go through the integer REDUX unit (sums cannot overflow).
+__device__ __forceinline__ long long warp_sum_s32(unsigned mask, int v) {
+  const unsigned lo = __reduce_add_sync(mask, (unsigned)(v & 0xffff));
+  const int hi = __reduce_add_sync(mask, v >> 16);
+  return ((long long)hi << 16) + (long long)lo;
+}
+
+// 64-bit add into a {lo, hi} pair of 32-bit shared-memory words.  The common
+// case is ONE native ATOMS.ADD (shared 64-bit and float atomics are CAS loops
+// on sm_100a); the carry / sign word is touched only when it changes.
+__device__ __forceinline__ void smem_add64(unsigned *lo, unsigned *hi, int il,
+                                           long long v) {
+  const unsigned uq = (unsigned)v;
+  const unsigned old = atomicAdd(&lo[il], uq);
+  const unsigned h = (unsigned)(v >> 32) + (old > ~uq ? 1u : 0u);
+  if (h) atomicAdd(&hi[il], h);
+}
+
+struct TrackSmem {
+  MathTables math;
+  unsigned long long w_cls[3];
+  unsigned int n_cls[3];
+  unsigned int pad;
+};
+
+// ----------------------------------------------------------- the hot path --
+
+template <bool SHARED, bool AGG>
+__global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TrackSmem *sm = reinterpret_cast<TrackSmem *>(smem_raw);
+  CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(TrackSmem));
+  unsigned *s_lo = reinterpret_cast<unsigned *>(s_xs + (SHARED ? p.m : 0));
+  unsigned *s_hi = s_lo + (SHARED ? p.m : 0);
+
+  load_math_tables(&sm->math);
+  if (threadIdx.x < 3) {
+    sm->w_cls[threadIdx.x] = 0ull;
+    sm->n_cls[threadIdx.x] = 0u;
+  }
+  if (SHARED) {
+    for (int c = threadIdx.x; c < p.m; c += blockDim.x) {
+      s_xs[c] = p.xs[c];
+      s_lo[c] = 0u;
+      s_hi[c] = 0u;
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int lo = p.idx_lo;
+  const int hi = p.idx_lo + p.m;
+  const float dx = p.dx, minw = p.minw, qscale = p.qscale;
+  const unsigned long long take = (unsigned long long)p.take_count;
+
+  // particle state, include/types/particle.hpp:7-18, one history per lane
+  unsigned long long seed = 0;
+  float x = 0.f, mu = 0.f, wmc = 0.f;
+  int idx = 0;
+  bool active = false;
+  bool exhausted = false;  // warp-uniform: the bank range has been handed out
+  unsigned n_ev = 0, n_sc = 0;
+
+  for (;;) {
+    // ---- liveness: loop condition of simulate_particle, src/layer.cpp:195-197
+    const bool alive = active && (wmc >= minw) && (idx >= lo) && (idx < hi);
+    const bool fin = active && !alive;
+    const unsigned fm = __ballot_sync(MCB_FULL, fin);
+    if (fm) {
+      // ---- retire: classification of src/layer.cpp:202-217, routing of
+      // :332-346, global-border absorption of :350-360
+      const int cls = (idx == lo - 1) ? 0 : (idx == hi) ? 1 : (wmc < minw) ? 2 : 0;
+      const int wq = __float2int_rn(__fmul_rn(wmc, qscale));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const bool mine = fin && cls == c;
+        const unsigned cm = __ballot_sync(MCB_FULL, mine);
+        if (cm == 0u) continue;
+        const int cnt = __popc(cm);
+        const int leader = __ffs(cm) - 1;
+        long long wsum = 0;
+        if (mine) wsum = warp_sum_s32(cm, wq);
+        if (lane == leader) {
+          atomicAdd(&sm->n_cls[c], (unsigned)cnt);
+          atomicAdd(&sm->w_cls[c], (unsigned long long)wsum);
+        }
+        if (c < 2 && p.write_side[c]) {
+          // warp-aggregated append: one reservation per warp, ranks by popc
+          unsigned long long base = 0ull;
+          if (lane == leader)
+            base = atomicAdd(&p.ctr->out_n[c], (unsigned long long)cnt);
+          base = __shfl_sync(MCB_FULL, base, leader);
+          if (mine) {
+            const long long pos = (long long)base + __popc(cm & lt_mask);
+            if (pos < p.out_cap[c]) {
+              p.out_seed[c][pos] = seed;
+              p.out_st[c][pos] = make_float4(x, mu, wmc, __int_as_float(idx));
+            } else {
+              atomicExch(&p.ctr->overflow, 1u);
+            }
+          }
+        }
+      }
+      active = active && !fin;
+    }
+
+    // ---- refill idle lanes from the bank (coalesced 8 B + 16 B per lane)
+    const unsigned im = __ballot_sync(MCB_FULL, !active);
+    if (im && !exhausted) {
+      const int cnt = __popc(im);
+      unsigned long long base = 0ull;
+      if (lane == 0) base = atomicAdd(&p.ctr->cursor, (unsigned long long)cnt);
+      base = __shfl_sync(MCB_FULL, base, 0);
+      if (base + (unsigned long long)cnt >= take) exhausted = true;
+      if (!active) {
+        const unsigned long long id = base + (unsigned long long)__popc(im & lt_mask);
+        if (id < take) {
+          const long long slot = p.take_base + (long long)id;
+          seed = __ldcs(&p.bank_seed[slot]);
+          const float4 st = __ldcs(&p.bank_st[slot]);
+          x = st.x;
+          mu = st.y;
+          wmc = st.z;
+          idx = __float_as_int(st.w);
+          active = true;
+        }
+      }
+      continue;  // fresh lanes go through the liveness test first
+    }
+    if (im == MCB_FULL) break;  // bank handed out and every lane retired
+
+    // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
+    const unsigned am = __ballot_sync(MCB_FULL, alive);
+    if (alive) {
+      const int il = idx - lo;                                   // :129
+      const CellXs xs = SHARED ? s_xs[il] : __ldg(&p.xs[il]);    // :131-133
+      seed = lcg_next(seed);                                     // :136
+      const float h = lcg_to_real(seed);
+      float di = MCB_MAXREAL;                                    // :137
+      if (xs.y > MCB_EPS) di = __fdiv_rn(-logf_glibc(h, &sm->math), xs.y);
+
+      const bool neg = mu < 0.0f;                                // :143-152
+      int inew = neg ? idx - 1 : idx + 1;
+      const float xe = __fmul_rn(__int2float_rn(neg ? idx : idx + 1), dx);
+      float de = MCB_MAXREAL;                                    // :154-158
+      if (mu < -MCB_EPS || MCB_EPS < mu) de = __fdiv_rn(__fsub_rn(xe, x), mu);
+
+      if (di < de) {                                             // :160-166
+        inew = idx;
+        x = __fadd_rn(x, __fmul_rn(di, mu));
+        seed = lcg_next(seed);
+        mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
+        ++n_sc;
+      } else {                                                   // :167-172
+        di = de;
+        x = xe;
+      }
+      const float e = expf_glibc_nonpos(__fmul_rn(-xs.x, di), &sm->math);
+      const float dw = __fmul_rn(__fsub_rn(1.0f, e), wmc);       // :175
+      wmc = __fsub_rn(wmc, dw);                                  // :178
+      // :179 weights_absorbed[il] += dw, as an exact fixed-point deposit
+      const int q = __float2int_rn(__fmul_rn(dw, qscale));
+      if (AGG) {
+        const unsigned peers = __match_any_sync(am, il);
+        const long long v = warp_sum_s32(peers, q);
+        if (lane == __ffs(peers) - 1) {
+          if (SHARED) smem_add64(s_lo, s_hi, il, v);
+          else atomicAdd(&p.tally_q[il], (unsigned long long)v);
+        }
+      } else {
+        if (SHARED) smem_add64(s_lo, s_hi, il, (long long)q);
+        else atomicAdd(&p.tally_q[il], (unsigned long long)(long long)q);
+      }
+      idx = inew;                                                // :181
+      ++n_ev;
+    }
+  }
+
+  // ---- per-CTA flush: one 64-bit RED per touched cell, counters once
+  unsigned long long ev = n_ev, sc = n_sc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ev += __shfl_xor_sync(MCB_FULL, ev, o);
+    sc += __shfl_xor_sync(MCB_FULL, sc, o);
+  }
+  if (lane == 0) {
+    if (ev) atomicAdd(&p.ctr->events, ev);
+    if (sc) atomicAdd(&p.ctr->scatters, sc);
+  }
+  __syncthreads();
+  if (SHARED) {
+    for (int c = threadIdx.x; c < p.m; c += blockDim.x) {
+      const unsigned long long v = ((unsigned long long)s_hi[c] << 32) | s_lo[c];
+      if (v) atomicAdd(&p.tally_q[c], v);
+    }
+  }
+  if (threadIdx.x < 3) {
+    const int c = threadIdx.x;
+    if (sm->n_cls[c]) atomicAdd(&p.ctr->n_cls[c], (unsigned long long)sm->n_cls[c]);
+    if (sm->w_cls[c])
+      atomicAdd(reinterpret_cast<unsigned long long *>(&p.ctr->w_cls_q[c]), sm->w_cls[c]);
+  }
+}
+
+size_t track_smem_bytes(int tally_mode, int m) {
+  size_t b = sizeof(TrackSmem);
+  if (tally_mode == kTallyShared) b += (size_t)m * (sizeof(CellXs) + 2 * sizeof(unsigned));
+  return b;
+}
+
+typedef void (*TrackFn)(const TrackParams);
+static TrackFn track_fn(int mode, int agg) {
+  if (mode == kTallyShared) return agg ? track_kernel<true, true> : track_kernel<true, false>;
+  return agg ? track_kernel<false, true> : track_kernel<false, false>;
+}
+
+cudaError_t track_configure(int device, int m, int want_mode, int want_agg,
+                            int want_block, int want_blocks_per_sm,
+                            TrackLaunch *out) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return e;
+  const size_t per_sm = prop.sharedMemPerMultiprocessor;   // 228 KB on B200
+  const size_t per_cta_max = prop.sharedMemPerBlockOptin;  // 227 KB
+  const size_t reserve = 1024;                             // driver reserve per CTA
+
+  int mode = want_mode;
+  if (mode != kTallyShared && mode != kTallyGlobal)
+    mode = track_smem_bytes(kTallyShared, m) <= per_cta_max ? kTallyShared : kTallyGlobal;
+  if (mode == kTallyShared && track_smem_bytes(kTallyShared, m) > per_cta_max)
+    return cudaErrorInvalidValue;
+  const size_t smem = track_smem_bytes(mode, m);
+
+  // 1024 resident threads per SM (register budget of the kernel: 64/thread);
+  // CTA shape chosen so that the CTA-private tally copies fit
+  int block = want_block > 0 ? want_block : 256;
+  int bps = want_blocks_per_sm > 0 ? want_blocks_per_sm : 1024 / block;
+  if (want_block <= 0 && want_blocks_per_sm <= 0) {
+    while (bps > 1 && (smem + reserve) * (size_t)bps > per_sm) {
+      bps /= 2;
+      block *= 2;
+    }
+  } else {
+    while (bps > 1 && (smem + reserve) * (size_t)bps > per_sm) --bps;
+  }
+  if (block > 1024 || block % 32) return cudaErrorInvalidValue;
+
+  out->tally_mode = mode;
+  out->warp_agg = want_agg ? 1 : 0;
+  out->block = block;
+  out->grid = prop.multiProcessorCount * bps;
+  out->smem = smem;
+  return cudaFuncSetAttribute(track_fn(mode, out->warp_agg),
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStream_t stream) {
+  if (p.take_count <= 0) return cudaSuccess;
+  long long need = (p.take_count + cfg.block - 1) / cfg.block;
+  int grid = (int)(need < (long long)cfg.grid ? need : (long long)cfg.grid);
+  track_fn(cfg.tally_mode, cfg.warp_agg)<<<grid, cfg.block, cfg.smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ birth --
+
+// Layer::create_particles(int n), src/layer.cpp:89-121, in parallel: the seed
+// chain state after k steps is an affine function of the start state, so
+// thread t jumps straight to particle t (63-entry table of squarings) and then
+// strides by the grid size with one precomputed multiply-add.
+__global__ void __launch_bounds__(256) birth_kernel(long long n, unsigned long long chain_state,
+                                                    const JumpTable jt, Affine stride_map,
+                                                    float x_ini, float wmc, int index,
+                                                    unsigned long long *__restrict__ seed_out,
+                                                    float4 *__restrict__ st_out) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  if (tid >= n) return;
+  // particle `tid` carries rnd_seed^(tid+1)(chain_state)   (:111)
+  unsigned long long s = jump_state(jt, (unsigned long long)tid + 1ull, chain_state);
+  for (long long i = tid; i < n; i += nthreads) {
+    unsigned long long ps = lcg_next(s);                               // :112 draw #1
+    const float mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(ps)), 1.0f);
+    __stcs(&seed_out[i], ps);
+    __stcs(&st_out[i], make_float4(x_ini, mu, wmc, __int_as_float(index)));
+    s = affine_apply(stride_map, s);
+  }
+}
+
+cudaError_t launch_birth(long long n, unsigned long long chain_state, const JumpTable &seed_jump,
+                         float x_ini, float wmc, int index, unsigned long long *seed_out,
+                         float4 *st_out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int block = 256;
+  long long want = (n + block - 1) / block;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  const Affine stride = jump_map(seed_jump, (unsigned long long)grid * block);
+  birth_kernel<<<grid, block, 0, stream>>>(n, chain_state, seed_jump, stride, x_ini, wmc, index,
+                                           seed_out, st_out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------- wire format <-> bank --
+
+// include/types/particle.hpp:7-18: {u64 seed; f32 x, mu, wmc; i32 index} = three
+// 8-byte words per record.
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(long long n,
+                                                         const unsigned long long *__restrict__ aos,
+                                                         unsigned long long *__restrict__ seed,
+                                                         float4 *__restrict__ st) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long a = __ldcs(&aos[3 * i]);
+    const unsigned long long b = __ldcs(&aos[3 * i + 1]);
+    const unsigned long long c = __ldcs(&aos[3 * i + 2]);
+    seed[i] = a;
+    st[i] = make_float4(__uint_as_float((unsigned)b), __uint_as_float((unsigned)(b >> 32)),
+                        __uint_as_float((unsigned)c), __uint_as_float((unsigned)(c >> 32)));
+  }
+}
+
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(long long n,
+                                                         const unsigned long long *__restrict__ seed,
+                                                         const float4 *__restrict__ st,
+                                                         unsigned long long *__restrict__ aos) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long a = seed[i];
+    const float4 s = st[i];
+    aos[3 * i] = a;
+    aos[3 * i + 1] = (unsigned long long)__float_as_uint(s.x) |
+                     ((unsigned long long)__float_as_uint(s.y) << 32);
+    aos[3 * i + 2] = (unsigned long long)__float_as_uint(s.z) |
+                     ((unsigned long long)__float_as_uint(s.w) << 32);
+  }
+}
+
+static int stream_grid(long long n, int block) {
+  long long want = (n + block - 1) / block;
+  return (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+}
+
+cudaError_t launch_aos_to_soa(long long n, const void *aos, unsigned long long *seed, float4 *st,
+                              cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  aos_to_soa_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(
+      n, static_cast<const unsigned long long *>(aos), seed, st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_soa_to_aos(long long n, const unsigned long long *seed, const float4 *st,
+                              void *aos, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  soa_to_aos_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(
+      n, seed, st, static_cast<unsigned long long *>(aos));
+  return cudaGetLastError();
+}
+
+// max of wmc over n bank entries; weights are non-negative so the float bits
+// order like unsigned integers and a plain atomicMax on the bits works
+__global__ void __launch_bounds__(256) max_wmc_kernel(long long n, const float4 *__restrict__ st,
+                                                      unsigned *__restrict__ out_bits) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    m = fmaxf(m, fabsf(st[i].z));
+  unsigned bits = __float_as_uint(m);
+  bits = __reduce_max_sync(MCB_FULL, bits);
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(out_bits, bits);
+}
+
+cudaError_t launch_max_wmc(long long n, const float4 *st, float *d_max_out, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_max_out, 0, sizeof(float), stream);
+  if (e != cudaSuccess || n <= 0) return e;
+  max_wmc_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(
+      n, st, reinterpret_cast<unsigned *>(d_max_out));
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------- known-answer kernels --
+
+// one rnd_real draw per element: the device counterpart of the reference's
+// rnd_real_kernel (src/curandom.cu:7-14)
+__global__ void test_rnd_real_kernel(long long n, unsigned long long *seeds, float *out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long s = lcg_next(seeds[i]);
+    seeds[i] = s;
+    out[i] = lcg_to_real(s);
+  }
+}
+
+cudaError_t launch_test_rnd_real(long long n, unsigned long long *seeds, float *out,
+                                 cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  test_rnd_real_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(n, seeds, out);
+  return cudaGetLastError();
+}
+
+__global__ void test_math_kernel(int which, long long n, const float *in, float *out) {
+  __shared__ MathTables tb;
+  load_math_tables(&tb);
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = which == 0 ? logf_glibc(in[i], &tb) : expf_glibc_nonpos(in[i], &tb);
+}
+
+cudaError_t launch_test_math(int which, long long n, const float *in, float *out,
+                             cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  test_math_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(which, n, in, out);
+  return cudaGetLastError();
+}
+
+}  // namespace mcb

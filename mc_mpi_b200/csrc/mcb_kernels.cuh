@@ -1,0 +1,93 @@
+// mcb_kernels.cuh -- device-side data structures + launch wrappers of the
+// tracking path (implemented in mcb_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "mcb_math.cuh"
+
+namespace mcb {
+
+// Device counters of one layer; zeroed per tracking launch, read back after.
+struct DevCounters {
+  unsigned long long cursor;      // next unclaimed slot of the launch's bank range
+  unsigned long long out_n[2];    // fill of the left / right outbox (persist across launches)
+  unsigned long long n_cls[3];    // histories classified left / right / dead
+  long long w_cls_q[3];           // their weights, fixed point (unit 2^-k)
+  unsigned long long events;
+  unsigned long long scatters;
+  unsigned int overflow;          // an outbox was too small (host sizes them so it cannot be)
+  unsigned int pad;
+};
+
+// per-cell constants of the event, precomputed once per layer from the public
+// sigs / absorption_rates vectors exactly as src/layer.cpp:131-133 does
+//   .x = sig_a = sigs*a          .y = sig_i = sigs*(float)(1.0 - a)
+typedef float2 CellXs;
+
+struct TrackParams {
+  // particle bank, structure of arrays of vectors: seed[] (8 B) and
+  // st[] = {x, mu, wmc, bits(index)} (16 B); every access is one coalesced
+  // 64-bit / 128-bit transaction per lane
+  const unsigned long long *bank_seed;
+  const float4 *bank_st;
+  long long take_base;   // first bank slot of this launch
+  long long take_count;  // number of particles to track
+  // the sub-slab
+  const CellXs *xs;      // m entries (global memory; staged to smem when it fits)
+  int idx_lo;            // Layer::index_start
+  int m;
+  float dx;
+  float minw;            // particle_min_weight
+  float qscale;          // 2^k, tally unit
+  // outputs
+  unsigned long long *tally_q;  // m fixed-point accumulators (two's complement)
+  unsigned long long *out_seed[2];
+  float4 *out_st[2];
+  long long out_cap[2];
+  int write_side[2];     // 0: global border, escapees are only counted
+  DevCounters *ctr;
+};
+
+enum TallyMode { kTallyShared = 1, kTallyGlobal = 2 };
+
+struct TrackLaunch {
+  int tally_mode;   // TallyMode
+  int warp_agg;     // 0/1
+  int block;        // threads per CTA
+  int grid;         // CTAs
+  size_t smem;      // dynamic shared memory bytes
+};
+
+// largest m whose tables + tally fit in shared memory for the given CTA shape
+size_t track_smem_bytes(int tally_mode, int m);
+cudaError_t track_configure(int device, int m, int want_mode, int want_agg,
+                            int want_block, int want_blocks_per_sm,
+                            TrackLaunch *out);
+cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg,
+                         cudaStream_t stream);
+
+// device-side birth (src/layer.cpp:101-120): particle i of the batch gets
+// seed = rnd_seed^(i+1)(chain_state), mu from the first rnd_real draw
+cudaError_t launch_birth(long long n, unsigned long long chain_state,
+                         const JumpTable &seed_jump, float x_ini, float wmc,
+                         int index, unsigned long long *seed_out, float4 *st_out,
+                         cudaStream_t stream);
+
+// 24-byte AoS records (include/types/particle.hpp) <-> bank layout
+cudaError_t launch_aos_to_soa(long long n, const void *aos,
+                              unsigned long long *seed, float4 *st,
+                              cudaStream_t stream);
+cudaError_t launch_soa_to_aos(long long n, const unsigned long long *seed,
+                              const float4 *st, void *aos, cudaStream_t stream);
+// max wmc of n bank entries (range guard of the fixed-point tally)
+cudaError_t launch_max_wmc(long long n, const float4 *st, float *d_max_out,
+                           cudaStream_t stream);
+
+// known-answer-test kernels
+cudaError_t launch_test_rnd_real(long long n, unsigned long long *seeds,
+                                 float *out, cudaStream_t stream);
+cudaError_t launch_test_math(int which, long long n, const float *in, float *out,
+                             cudaStream_t stream);
+
+}  // namespace mcb

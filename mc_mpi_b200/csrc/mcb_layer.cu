@@ -1,0 +1,772 @@
+// mcb_layer.cu -- host side of one layer (= one sub-slab on one GPU) and the
+// C ABI of include/mcb200.h.  Mirrors the state machine of the reference's
+// Layer (include/layer/layer.hpp, src/layer.cpp) with the bank, the outboxes
+// and the tally resident in HBM:
+//
+//   bank      seed[cap] (u64) + st[cap] (float4 {x, mu, wmc, bits(index)})
+//   outboxes  same layout, one per side, filled by the tracking kernel
+//   tally     u64[m] fixed point, unit 2^-k       xs  float2[m] {sig_a, sig_i}
+//
+// Nothing here computes physics on the CPU: there is no fallback path.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mcb200.h"
+#include "mcb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define MCB_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(e__ == cudaErrorMemoryAllocation ? MCB200_ERR_NOMEM : MCB200_ERR_CUDA, \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// growable pair of device arrays in the bank layout
+struct SoaBuf {
+  unsigned long long *seed = nullptr;
+  float4 *st = nullptr;
+  long long cap = 0;
+};
+
+}  // namespace
+
+struct mcb200_layer {
+  // --- what Layer carries (include/layer/layer.hpp:85-109)
+  int device = 0;
+  float x_min = 0, x_max = 0;
+  int index_start = 0, m = 0;
+  float dx = 0;
+  float particle_min_weight = 0;
+  bool left_border = false, right_border = false;
+  bool keep_border = false;
+  std::vector<float> sigs, absorption_rates;
+  long long nb_disabled = 0;
+  // unborn source particles (layer.hpp:107-109)
+  unsigned long long chain_state = 0;
+  float x_ini = 0, wmc = 0;
+  long long n_unborn = 0;
+  // --- fixed-point tally
+  float wmc_max = 0;
+  int log2_scale = 0;
+  // --- device state
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  SoaBuf bank;
+  long long n_bank = 0;
+  SoaBuf outbox[2];
+  long long n_out[2] = {0, 0};
+  mcb::CellXs *d_xs = nullptr;
+  unsigned long long *d_tally = nullptr;
+  mcb::DevCounters *d_ctr = nullptr;
+  mcb::DevCounters *h_ctr = nullptr;  // pinned
+  void *d_stage = nullptr;            // AoS staging for push / pop
+  long long stage_cap = 0;            // in particles
+  float *d_scalar = nullptr;
+  bool xs_dirty = true;
+  mcb::JumpTable seed_jump;
+  // --- knobs / cumulative stats
+  int opt_tally_mode = 0, opt_warp_agg = 0, opt_block = 0, opt_bps = 0;
+  long long opt_birth_chunk = 1ll << 26;
+  bool cfg_dirty = true;
+  mcb::TrackLaunch cfg{};
+  long long events = 0, scatters = 0, n_cls[3] = {0, 0, 0};
+  long long w_cls_q[3] = {0, 0, 0};
+  long long launches = 0, gpu_launches = 0;
+  double track_ms = 0;
+};
+
+namespace {
+
+int soa_reserve(mcb200_layer *l, SoaBuf *b, long long used, long long want) {
+  if (want <= b->cap) return MCB200_OK;
+  long long cap = b->cap > 0 ? b->cap : 4096;
+  while (cap < want) cap += cap / 2 + 1;
+  unsigned long long *ns = nullptr;
+  float4 *nt = nullptr;
+  MCB_CUDA(cudaMalloc(&ns, (size_t)cap * sizeof(unsigned long long)));
+  cudaError_t e = cudaMalloc(&nt, (size_t)cap * sizeof(float4));
+  if (e != cudaSuccess) {
+    cudaFree(ns);
+    return fail(MCB200_ERR_NOMEM, std::string("cudaMalloc bank: ") + cudaGetErrorString(e));
+  }
+  if (used > 0) {
+    MCB_CUDA(cudaMemcpyAsync(ns, b->seed, (size_t)used * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToDevice, l->stream));
+    MCB_CUDA(cudaMemcpyAsync(nt, b->st, (size_t)used * sizeof(float4), cudaMemcpyDeviceToDevice,
+                             l->stream));
+    MCB_CUDA(cudaStreamSynchronize(l->stream));
+  }
+  cudaFree(b->seed);
+  cudaFree(b->st);
+  b->seed = ns;
+  b->st = nt;
+  b->cap = cap;
+  return MCB200_OK;
+}
+
+int stage_reserve(mcb200_layer *l, long long n) {
+  if (n <= l->stage_cap) return MCB200_OK;
+  long long cap = l->stage_cap > 0 ? l->stage_cap : 4096;
+  while (cap < n) cap += cap / 2 + 1;
+  if (l->d_stage) cudaFree(l->d_stage);
+  l->d_stage = nullptr;
+  l->stage_cap = 0;
+  MCB_CUDA(cudaMalloc(&l->d_stage, (size_t)cap * sizeof(mcb200_particle)));
+  l->stage_cap = cap;
+  return MCB200_OK;
+}
+
+// per-cell event constants, src/layer.cpp:131-133 (host x86-64 code is built
+// without FMA contraction, like the reference)
+int upload_xs(mcb200_layer *l) {
+  std::vector<mcb::CellXs> xs((size_t)l->m);
+  for (int i = 0; i < l->m; ++i) {
+    const float a = l->absorption_rates[(size_t)i];
+    const float interaction_rate = (float)(1.0 - (double)a);
+    volatile float sig_a = l->sigs[(size_t)i] * a;
+    volatile float sig_i = l->sigs[(size_t)i] * interaction_rate;
+    xs[(size_t)i] = make_float2(sig_a, sig_i);
+  }
+  MCB_CUDA(cudaMemcpyAsync(l->d_xs, xs.data(), xs.size() * sizeof(mcb::CellXs),
+                           cudaMemcpyHostToDevice, l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  l->xs_dirty = false;
+  return MCB200_OK;
+}
+
+int fetch_tally(mcb200_layer *l, std::vector<long long> *out) {
+  out->resize((size_t)l->m);
+  DeviceGuard g(l->device);
+  MCB_CUDA(cudaMemcpyAsync(out->data(), l->d_tally, (size_t)l->m * sizeof(long long),
+                           cudaMemcpyDeviceToHost, l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  return MCB200_OK;
+}
+
+// Layer::create_particles(int n), src/layer.cpp:89-121, on the device
+int birth(mcb200_layer *l, long long n) {
+  if (n <= 0) return MCB200_OK;
+  int rc = soa_reserve(l, &l->bank, l->n_bank, l->n_bank + n);
+  if (rc) return rc;
+  volatile float cell = l->x_ini / l->dx;  // :106, ignores x_min
+  const int index = (int)cell;
+  MCB_CUDA(mcb::launch_birth(n, l->chain_state, l->seed_jump, l->x_ini, l->wmc, index,
+                             l->bank.seed + l->n_bank, l->bank.st + l->n_bank, l->stream));
+  l->gpu_launches++;
+  l->chain_state = mcb::jump_state(l->seed_jump, (unsigned long long)n, l->chain_state);
+  l->n_bank += n;
+  l->n_unborn -= n;
+  return MCB200_OK;
+}
+
+int track(mcb200_layer *l, long long take) {
+  if (take <= 0) return MCB200_OK;
+  if (l->xs_dirty) {
+    int rc = upload_xs(l);
+    if (rc) return rc;
+  }
+  if (l->cfg_dirty) {
+    MCB_CUDA(mcb::track_configure(l->device, l->m, l->opt_tally_mode, l->opt_warp_agg,
+                                  l->opt_block, l->opt_bps, &l->cfg));
+    l->cfg_dirty = false;
+  }
+  const bool write_side[2] = {!l->left_border || l->keep_border,
+                              !l->right_border || l->keep_border};
+  for (int s = 0; s < 2; ++s) {
+    if (!write_side[s]) continue;
+    int rc = soa_reserve(l, &l->outbox[s], l->n_out[s], l->n_out[s] + take);
+    if (rc) return rc;
+  }
+  // counters: everything per-launch is zeroed, the outbox fills persist
+  std::memset(l->h_ctr, 0, sizeof(mcb::DevCounters));
+  l->h_ctr->out_n[0] = (unsigned long long)l->n_out[0];
+  l->h_ctr->out_n[1] = (unsigned long long)l->n_out[1];
+  MCB_CUDA(cudaMemcpyAsync(l->d_ctr, l->h_ctr, sizeof(mcb::DevCounters), cudaMemcpyHostToDevice,
+                           l->stream));
+  mcb::TrackParams p{};
+  p.bank_seed = l->bank.seed;
+  p.bank_st = l->bank.st;
+  p.take_base = l->n_bank - take;  // the LAST `take` of the bank, src/layer.cpp:319
+  p.take_count = take;
+  p.xs = l->d_xs;
+  p.idx_lo = l->index_start;
+  p.m = l->m;
+  p.dx = l->dx;
+  p.minw = l->particle_min_weight;
+  p.qscale = std::ldexp(1.0f, l->log2_scale);
+  p.tally_q = l->d_tally;
+  for (int s = 0; s < 2; ++s) {
+    p.out_seed[s] = l->outbox[s].seed;
+    p.out_st[s] = l->outbox[s].st;
+    p.out_cap[s] = l->outbox[s].cap;
+    p.write_side[s] = write_side[s] ? 1 : 0;
+  }
+  p.ctr = l->d_ctr;
+  MCB_CUDA(cudaEventRecord(l->ev0, l->stream));
+  MCB_CUDA(mcb::launch_track(p, l->cfg, l->stream));
+  MCB_CUDA(cudaEventRecord(l->ev1, l->stream));
+  MCB_CUDA(cudaMemcpyAsync(l->h_ctr, l->d_ctr, sizeof(mcb::DevCounters), cudaMemcpyDeviceToHost,
+                           l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  float ms = 0.f;
+  MCB_CUDA(cudaEventElapsedTime(&ms, l->ev0, l->ev1));
+  l->track_ms += ms;
+  l->launches++;
+  l->gpu_launches++;
+  if (l->h_ctr->overflow) return fail(MCB200_ERR_CAPACITY, "internal: outbox overflow");
+
+  const mcb::DevCounters &c = *l->h_ctr;
+  l->n_bank -= take;
+  l->events += (long long)c.events;
+  l->scatters += (long long)c.scatters;
+  for (int k = 0; k < 3; ++k) {
+    l->n_cls[k] += (long long)c.n_cls[k];
+    l->w_cls_q[k] += c.w_cls_q[k];
+  }
+  l->n_out[0] = (long long)c.out_n[0];
+  l->n_out[1] = (long long)c.out_n[1];
+  // src/layer.cpp:343 (dead) and :350-360 (global borders absorb)
+  l->nb_disabled += (long long)c.n_cls[2];
+  if (l->left_border) l->nb_disabled += (long long)c.n_cls[0];
+  if (l->right_border) l->nb_disabled += (long long)c.n_cls[1];
+  return MCB200_OK;
+}
+
+int fill_counts(mcb200_layer *l, mcb200_counts *o) {
+  if (!o) return MCB200_OK;
+  const double unit = std::ldexp(1.0, -l->log2_scale);
+  o->nb_disabled = l->nb_disabled;
+  o->nb_active = l->n_bank + l->n_unborn;
+  o->n_bank = l->n_bank;
+  o->n_unborn = l->n_unborn;
+  o->n_outbox_left = l->n_out[0];
+  o->n_outbox_right = l->n_out[1];
+  o->events = l->events;
+  o->scatters = l->scatters;
+  o->n_left = l->n_cls[0];
+  o->n_right = l->n_cls[1];
+  o->n_dead = l->n_cls[2];
+  o->w_left = (double)l->w_cls_q[0] * unit;
+  o->w_right = (double)l->w_cls_q[1] * unit;
+  o->w_dead = (double)l->w_cls_q[2] * unit;
+  o->launches = l->launches;
+  o->track_ms = l->track_ms;
+  o->gpu_launches = l->gpu_launches;
+  return MCB200_OK;
+}
+
+// range guard of the fixed-point tally: every weight must be <= wmc_max
+int check_wmc(mcb200_layer *l, long long first, long long n) {
+  if (n <= 0) return MCB200_OK;
+  MCB_CUDA(mcb::launch_max_wmc(n, l->bank.st + first, l->d_scalar, l->stream));
+  l->gpu_launches++;
+  float mx = 0.f;
+  MCB_CUDA(cudaMemcpyAsync(&mx, l->d_scalar, sizeof(float), cudaMemcpyDeviceToHost, l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  if (!(mx <= l->wmc_max)) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "particle weight %.9g exceeds the layer's wmc_max %.9g", mx,
+                  l->wmc_max);
+    return fail(MCB200_ERR_RANGE, buf);
+  }
+  return MCB200_OK;
+}
+
+int pop_side(mcb200_layer *l, int side, void *dst, bool dst_is_device, long long cap,
+             long long *n_out) {
+  if (!l || !n_out || (cap > 0 && !dst)) return fail(MCB200_ERR_INVALID, "pop: null argument");
+  DeviceGuard g(l->device);
+  const long long n = l->n_out[side];
+  if (n > cap) {
+    *n_out = n;
+    return fail(MCB200_ERR_CAPACITY, "pop: caller buffer too small");
+  }
+  if (n > 0) {
+    void *aos = dst;
+    if (!dst_is_device) {
+      int rc = stage_reserve(l, n);
+      if (rc) return rc;
+      aos = l->d_stage;
+    }
+    MCB_CUDA(mcb::launch_soa_to_aos(n, l->outbox[side].seed, l->outbox[side].st, aos, l->stream));
+    l->gpu_launches++;
+    if (!dst_is_device)
+      MCB_CUDA(cudaMemcpyAsync(dst, aos, (size_t)n * sizeof(mcb200_particle),
+                               cudaMemcpyDeviceToHost, l->stream));
+    MCB_CUDA(cudaStreamSynchronize(l->stream));
+  }
+  l->n_out[side] = 0;
+  *n_out = n;
+  return MCB200_OK;
+}
+
+int push_any(mcb200_layer *l, const void *src, bool src_is_device, long long n) {
+  if (!l || n < 0 || (n > 0 && !src)) return fail(MCB200_ERR_INVALID, "push: bad argument");
+  if (n == 0) return MCB200_OK;
+  DeviceGuard g(l->device);
+  int rc = soa_reserve(l, &l->bank, l->n_bank, l->n_bank + n);
+  if (rc) return rc;
+  const void *aos = src;
+  if (!src_is_device) {
+    rc = stage_reserve(l, n);
+    if (rc) return rc;
+    MCB_CUDA(cudaMemcpyAsync(l->d_stage, src, (size_t)n * sizeof(mcb200_particle),
+                             cudaMemcpyHostToDevice, l->stream));
+    aos = l->d_stage;
+  }
+  MCB_CUDA(mcb::launch_aos_to_soa(n, aos, l->bank.seed + l->n_bank, l->bank.st + l->n_bank,
+                                  l->stream));
+  l->gpu_launches++;
+  rc = check_wmc(l, l->n_bank, n);
+  if (rc) return rc;
+  l->n_bank += n;
+  return MCB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mcb200_last_error(void) { return g_last_error.c_str(); }
+int mcb200_abi_version(void) { return MCB200_ABI_VERSION; }
+int mcb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
+  if (!d || !out) return fail(MCB200_ERR_INVALID, "create: null argument");
+  *out = nullptr;
+  if (d->abi_version != MCB200_ABI_VERSION)
+    return fail(MCB200_ERR_INVALID, "create: abi_version mismatch");
+  if (d->m <= 0) return fail(MCB200_ERR_INVALID, "create: m must be positive");
+  if (!(d->wmc_max > 0.0f) || !std::isfinite(d->wmc_max))
+    return fail(MCB200_ERR_INVALID, "create: wmc_max must be a positive finite weight bound");
+  int ndev = 0;
+  MCB_CUDA(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev)
+    return fail(MCB200_ERR_INVALID, "create: no such CUDA device");
+
+  mcb200_layer *l = new (std::nothrow) mcb200_layer();
+  if (!l) return fail(MCB200_ERR_NOMEM, "create: out of host memory");
+  l->device = d->device;
+  l->x_min = d->x_min;
+  l->x_max = d->x_max;
+  l->index_start = d->index_start;
+  l->m = d->m;
+  {
+    volatile float w = (d->x_max - d->x_min) / d->m;  // src/layer.cpp:47
+    l->dx = d->dx > 0.0f ? d->dx : w;
+  }
+  l->particle_min_weight = d->particle_min_weight;
+  l->left_border = d->left_border < 0 ? std::fabs((double)d->x_min) < (double)MCB_EPS
+                                      : d->left_border != 0;
+  l->right_border = d->right_border < 0 ? std::fabs((double)d->x_max - 1.0) < (double)MCB_EPS
+                                        : d->right_border != 0;
+  l->keep_border = d->keep_border != 0;
+  l->sigs.resize((size_t)l->m);
+  l->absorption_rates.resize((size_t)l->m);
+  // cross-sections default to the reference's hard-coded ones (src/layer.cpp:53-63)
+  {
+    volatile float w = (d->x_max - d->x_min) / d->m;  // the ctor's own dx, :47
+    const float ldx = w;
+    for (int i = 0; i < l->m; ++i) {
+      volatile float base = d->x_min + (i * ldx);
+      const float x_mid = (float)((double)base + 0.5 * (double)ldx);  // :58
+      l->sigs[(size_t)i] = d->sigs ? d->sigs[i] : expf(-x_mid);        // :59
+      l->absorption_rates[(size_t)i] = d->absorption_rates ? d->absorption_rates[i] : 0.5f;
+    }
+  }
+  l->wmc_max = d->wmc_max;
+  {
+    int e = 0;
+    std::frexp(d->wmc_max, &e);  // wmc_max = f * 2^e, f in [0.5, 1)
+    l->log2_scale = 30 - e;      // wmc_max * 2^k in [2^29, 2^30)
+  }
+  l->seed_jump = mcb::make_jump_table(mcb::kSeedG, mcb::kSeedC);
+
+  DeviceGuard g(l->device);
+  int rc = MCB200_OK;
+  auto cuda_ok = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess && rc == MCB200_OK)
+      rc = fail(e == cudaErrorMemoryAllocation ? MCB200_ERR_NOMEM : MCB200_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  cuda_ok(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_ok(cudaEventCreate(&l->ev0), "cudaEventCreate");
+  cuda_ok(cudaEventCreate(&l->ev1), "cudaEventCreate");
+  cuda_ok(cudaMalloc(&l->d_xs, (size_t)l->m * sizeof(mcb::CellXs)), "cudaMalloc xs");
+  cuda_ok(cudaMalloc(&l->d_tally, (size_t)l->m * sizeof(unsigned long long)), "cudaMalloc tally");
+  cuda_ok(cudaMalloc(&l->d_ctr, sizeof(mcb::DevCounters)), "cudaMalloc counters");
+  cuda_ok(cudaMalloc(&l->d_scalar, 16), "cudaMalloc scalar");
+  cuda_ok(cudaMallocHost(&l->h_ctr, sizeof(mcb::DevCounters)), "cudaMallocHost counters");
+  if (rc == MCB200_OK)
+    cuda_ok(cudaMemsetAsync(l->d_tally, 0, (size_t)l->m * sizeof(unsigned long long), l->stream),
+            "cudaMemset tally");
+  if (rc == MCB200_OK) cuda_ok(cudaStreamSynchronize(l->stream), "cudaStreamSynchronize");
+  if (rc != MCB200_OK) {
+    std::string keep = g_last_error;
+    mcb200_layer_destroy(l);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = l;
+  return MCB200_OK;
+}
+
+void mcb200_layer_destroy(mcb200_layer *l) {
+  if (!l) return;
+  {
+    DeviceGuard g(l->device);
+    if (l->stream) cudaStreamSynchronize(l->stream);
+    cudaFree(l->bank.seed);
+    cudaFree(l->bank.st);
+    for (int s = 0; s < 2; ++s) {
+      cudaFree(l->outbox[s].seed);
+      cudaFree(l->outbox[s].st);
+    }
+    cudaFree(l->d_xs);
+    cudaFree(l->d_tally);
+    cudaFree(l->d_ctr);
+    cudaFree(l->d_stage);
+    cudaFree(l->d_scalar);
+    if (l->h_ctr) cudaFreeHost(l->h_ctr);
+    if (l->ev0) cudaEventDestroy(l->ev0);
+    if (l->ev1) cudaEventDestroy(l->ev1);
+    if (l->stream) cudaStreamDestroy(l->stream);
+    cudaGetLastError();
+  }
+  delete l;
+}
+
+int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
+  if (!src || !out) return fail(MCB200_ERR_INVALID, "clone: null argument");
+  *out = nullptr;
+  mcb200_layer_desc d{};
+  d.abi_version = MCB200_ABI_VERSION;
+  d.device = src->device;
+  d.x_min = src->x_min;
+  d.x_max = src->x_max;
+  d.index_start = src->index_start;
+  d.m = src->m;
+  d.dx = src->dx;
+  d.particle_min_weight = src->particle_min_weight;
+  d.left_border = src->left_border;
+  d.right_border = src->right_border;
+  d.sigs = src->sigs.data();
+  d.absorption_rates = src->absorption_rates.data();
+  d.wmc_max = src->wmc_max;
+  d.keep_border = src->keep_border;
+  mcb200_layer *l = nullptr;
+  int rc = mcb200_layer_create(&d, &l);
+  if (rc) return rc;
+  DeviceGuard g(l->device);
+  auto bail = [&](int code) {
+    std::string keep = g_last_error;
+    mcb200_layer_destroy(l);
+    g_last_error = keep;
+    return code;
+  };
+  cudaStreamSynchronize(src->stream);
+  const SoaBuf *from[3] = {&src->bank, &src->outbox[0], &src->outbox[1]};
+  SoaBuf *to[3] = {&l->bank, &l->outbox[0], &l->outbox[1]};
+  const long long used[3] = {src->n_bank, src->n_out[0], src->n_out[1]};
+  for (int k = 0; k < 3; ++k) {
+    if (used[k] <= 0) continue;
+    rc = soa_reserve(l, to[k], 0, used[k]);
+    if (rc) return bail(rc);
+    if (cudaMemcpyAsync(to[k]->seed, from[k]->seed, (size_t)used[k] * 8, cudaMemcpyDeviceToDevice,
+                        l->stream) != cudaSuccess ||
+        cudaMemcpyAsync(to[k]->st, from[k]->st, (size_t)used[k] * 16, cudaMemcpyDeviceToDevice,
+                        l->stream) != cudaSuccess)
+      return bail(fail(MCB200_ERR_CUDA, "clone: device copy failed"));
+  }
+  if (cudaMemcpyAsync(l->d_tally, src->d_tally, (size_t)l->m * 8, cudaMemcpyDeviceToDevice,
+                      l->stream) != cudaSuccess ||
+      cudaStreamSynchronize(l->stream) != cudaSuccess)
+    return bail(fail(MCB200_ERR_CUDA, "clone: device copy failed"));
+  l->n_bank = src->n_bank;
+  l->n_out[0] = src->n_out[0];
+  l->n_out[1] = src->n_out[1];
+  l->nb_disabled = src->nb_disabled;
+  l->chain_state = src->chain_state;
+  l->x_ini = src->x_ini;
+  l->wmc = src->wmc;
+  l->n_unborn = src->n_unborn;
+  l->opt_tally_mode = src->opt_tally_mode;
+  l->opt_warp_agg = src->opt_warp_agg;
+  l->opt_block = src->opt_block;
+  l->opt_bps = src->opt_bps;
+  l->opt_birth_chunk = src->opt_birth_chunk;
+  l->events = src->events;
+  l->scatters = src->scatters;
+  for (int k = 0; k < 3; ++k) {
+    l->n_cls[k] = src->n_cls[k];
+    l->w_cls_q[k] = src->w_cls_q[k];
+  }
+  l->launches = src->launches;
+  l->gpu_launches = src->gpu_launches;
+  l->track_ms = src->track_ms;
+  *out = l;
+  return MCB200_OK;
+}
+
+int mcb200_layer_set_cross_sections(mcb200_layer *l, const float *sigs,
+                                    const float *absorption_rates) {
+  if (!l) return fail(MCB200_ERR_INVALID, "set_cross_sections: null layer");
+  if (sigs) l->sigs.assign(sigs, sigs + l->m);
+  if (absorption_rates) l->absorption_rates.assign(absorption_rates, absorption_rates + l->m);
+  l->xs_dirty = true;
+  return MCB200_OK;
+}
+
+int mcb200_layer_get_cross_sections(mcb200_layer *l, float *sigs_out, float *absorption_rates_out) {
+  if (!l) return fail(MCB200_ERR_INVALID, "get_cross_sections: null layer");
+  if (sigs_out) std::memcpy(sigs_out, l->sigs.data(), (size_t)l->m * sizeof(float));
+  if (absorption_rates_out)
+    std::memcpy(absorption_rates_out, l->absorption_rates.data(), (size_t)l->m * sizeof(float));
+  return MCB200_OK;
+}
+
+int mcb200_layer_create_particles(mcb200_layer *l, float x_ini, float wmc, int64_t n,
+                                  uint64_t seed) {
+  if (!l || n < 0) return fail(MCB200_ERR_INVALID, "create_particles: bad argument");
+  if (!(x_ini > l->x_min && x_ini < l->x_max)) return MCB200_OK;  // src/layer.cpp:73
+  if (!(wmc <= l->wmc_max) || wmc < 0.0f)
+    return fail(MCB200_ERR_RANGE, "create_particles: wmc outside [0, wmc_max]");
+  l->x_ini = x_ini;  // :75-78
+  l->wmc = wmc;
+  l->n_unborn = n;
+  l->chain_state = seed;
+  return MCB200_OK;
+}
+
+int mcb200_layer_push(mcb200_layer *l, const mcb200_particle *aos, int64_t n) {
+  return push_any(l, aos, false, n);
+}
+int mcb200_layer_push_device(mcb200_layer *l, const void *dev_aos, int64_t n) {
+  return push_any(l, dev_aos, true, n);
+}
+
+int mcb200_layer_simulate(mcb200_layer *l, int64_t nb_particles, mcb200_counts *counts) {
+  if (!l) return fail(MCB200_ERR_INVALID, "simulate: null layer");
+  DeviceGuard g(l->device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "simulate: cudaSetDevice failed");
+  long long want = nb_particles < 0 ? l->n_bank + l->n_unborn : (long long)nb_particles;
+  if (want > l->n_bank + l->n_unborn) want = l->n_bank + l->n_unborn;
+  while (want > 0) {
+    // src/layer.cpp:244-245: births top the bank up when it holds fewer than asked
+    if (l->n_bank < want && l->n_unborn > 0) {
+      long long nb = want - l->n_bank;
+      if (nb > l->n_unborn) nb = l->n_unborn;
+      if (nb > l->opt_birth_chunk) nb = l->opt_birth_chunk;
+      int rc = birth(l, nb);
+      if (rc) return rc;
+    }
+    long long take = want < l->n_bank ? want : l->n_bank;
+    // keep launches bounded by the birth chunk so outboxes stay bounded too
+    if (take > l->opt_birth_chunk) take = l->opt_birth_chunk;
+    if (take <= 0) break;
+    int rc = track(l, take);
+    if (rc) return rc;
+    want -= take;
+  }
+  return fill_counts(l, counts);
+}
+
+int mcb200_layer_counts(mcb200_layer *l, mcb200_counts *out) {
+  if (!l || !out) return fail(MCB200_ERR_INVALID, "counts: null argument");
+  return fill_counts(l, out);
+}
+
+int mcb200_layer_pop_left(mcb200_layer *l, mcb200_particle *aos, int64_t cap, int64_t *n_out) {
+  long long n = 0;
+  int rc = pop_side(l, 0, aos, false, cap, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+int mcb200_layer_pop_right(mcb200_layer *l, mcb200_particle *aos, int64_t cap, int64_t *n_out) {
+  long long n = 0;
+  int rc = pop_side(l, 1, aos, false, cap, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+int mcb200_layer_pop_left_device(mcb200_layer *l, void *dev_aos, int64_t cap, int64_t *n_out) {
+  long long n = 0;
+  int rc = pop_side(l, 0, dev_aos, true, cap, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap, int64_t *n_out) {
+  long long n = 0;
+  int rc = pop_side(l, 1, dev_aos, true, cap, &n);
+  if (n_out) *n_out = n;
+  return rc;
+}
+
+int mcb200_layer_weights_absorbed_q(mcb200_layer *l, int64_t *out_m, int32_t *log2_scale) {
+  if (!l || !out_m) return fail(MCB200_ERR_INVALID, "weights_absorbed_q: null argument");
+  std::vector<long long> q;
+  int rc = fetch_tally(l, &q);
+  if (rc) return rc;
+  for (int i = 0; i < l->m; ++i) out_m[i] = q[(size_t)i];
+  if (log2_scale) *log2_scale = l->log2_scale;
+  return MCB200_OK;
+}
+
+int mcb200_layer_weights_absorbed_f64(mcb200_layer *l, double *out_m) {
+  if (!l || !out_m) return fail(MCB200_ERR_INVALID, "weights_absorbed_f64: null argument");
+  std::vector<long long> q;
+  int rc = fetch_tally(l, &q);
+  if (rc) return rc;
+  const double unit = std::ldexp(1.0, -l->log2_scale);
+  for (int i = 0; i < l->m; ++i) out_m[i] = (double)q[(size_t)i] * unit;
+  return MCB200_OK;
+}
+
+int mcb200_layer_weights_absorbed(mcb200_layer *l, float *out_m) {
+  if (!l || !out_m) return fail(MCB200_ERR_INVALID, "weights_absorbed: null argument");
+  std::vector<long long> q;
+  int rc = fetch_tally(l, &q);
+  if (rc) return rc;
+  const double unit = std::ldexp(1.0, -l->log2_scale);
+  for (int i = 0; i < l->m; ++i) out_m[i] = (float)((double)q[(size_t)i] * unit);
+  return MCB200_OK;
+}
+
+int mcb200_layer_dump_WA(mcb200_layer *l, const char *path) {
+  if (!l) return fail(MCB200_ERR_INVALID, "dump_WA: null layer");
+  std::vector<float> w((size_t)l->m);
+  int rc = mcb200_layer_weights_absorbed(l, w.data());
+  if (rc) return rc;
+  FILE *f = std::fopen(path ? path : "WA.out", "w");
+  if (!f) return fail(MCB200_ERR_INVALID, "Couldn't open file WA.out for writing.");
+  volatile float wdx = (l->x_max - l->x_min) / l->m;  // the reference prints with Layer::dx
+  const float ldx = wdx;
+  for (int i = 0; i < l->m; ++i) {  // src/layer.cpp:373-377
+    volatile float base = l->x_min + (i * ldx);
+    volatile float ratio = w[(size_t)i] / ldx;
+    std::fprintf(f, "%.4e %.3e\n", (double)base + 0.5 * (double)ldx, (double)ratio);
+  }
+  std::fclose(f);
+  return MCB200_OK;
+}
+
+void *mcb200_layer_stream(mcb200_layer *l) { return l ? (void *)l->stream : nullptr; }
+
+int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value) {
+  if (!l || !key) return fail(MCB200_ERR_INVALID, "set_option: null argument");
+  const std::string k(key);
+  if (k == "tally_mode") l->opt_tally_mode = (int)value;
+  else if (k == "warp_agg") l->opt_warp_agg = (int)value;
+  else if (k == "block") l->opt_block = (int)value;
+  else if (k == "blocks_per_sm") l->opt_bps = (int)value;
+  else if (k == "birth_chunk") {
+    if (value <= 0) return fail(MCB200_ERR_INVALID, "set_option: birth_chunk must be positive");
+    l->opt_birth_chunk = value;
+  } else
+    return fail(MCB200_ERR_INVALID, "set_option: unknown key " + k);
+  l->cfg_dirty = true;
+  return MCB200_OK;
+}
+
+// ---- known-answer-test entry points ------------------------------------
+
+int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host, int64_t n) {
+  if (n < 0 || (n > 0 && (!seeds_host || !out_host)))
+    return fail(MCB200_ERR_INVALID, "test_rnd_real: bad argument");
+  if (n == 0) return MCB200_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "test_rnd_real: cudaSetDevice failed");
+  unsigned long long *ds = nullptr;
+  float *dout = nullptr;
+  MCB_CUDA(cudaMalloc(&ds, (size_t)n * 8));
+  MCB_CUDA(cudaMalloc(&dout, (size_t)n * 4));
+  MCB_CUDA(cudaMemcpy(ds, seeds_host, (size_t)n * 8, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_rnd_real(n, ds, dout, nullptr));
+  MCB_CUDA(cudaMemcpy(seeds_host, ds, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  MCB_CUDA(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(ds);
+  cudaFree(dout);
+  return MCB200_OK;
+}
+
+static int test_math(int which, int device, const float *in_host, float *out_host, int64_t n) {
+  if (n < 0 || (n > 0 && (!in_host || !out_host)))
+    return fail(MCB200_ERR_INVALID, "test_math: bad argument");
+  if (n == 0) return MCB200_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "test_math: cudaSetDevice failed");
+  float *din = nullptr, *dout = nullptr;
+  MCB_CUDA(cudaMalloc(&din, (size_t)n * 4));
+  MCB_CUDA(cudaMalloc(&dout, (size_t)n * 4));
+  MCB_CUDA(cudaMemcpy(din, in_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_math(which, n, din, dout, nullptr));
+  MCB_CUDA(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(din);
+  cudaFree(dout);
+  return MCB200_OK;
+}
+int mcb200_test_logf(int device, const float *in_host, float *out_host, int64_t n) {
+  return test_math(0, device, in_host, out_host, n);
+}
+int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t n) {
+  return test_math(1, device, in_host, out_host, n);
+}
+
+int mcb200_test_birth(int device, float x_ini, float wmc, float dx, int64_t n, uint64_t seed,
+                      mcb200_particle *out_host) {
+  if (n < 0 || (n > 0 && !out_host)) return fail(MCB200_ERR_INVALID, "test_birth: bad argument");
+  if (n == 0) return MCB200_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "test_birth: cudaSetDevice failed");
+  unsigned long long *ds = nullptr;
+  float4 *dst = nullptr;
+  void *daos = nullptr;
+  MCB_CUDA(cudaMalloc(&ds, (size_t)n * 8));
+  MCB_CUDA(cudaMalloc(&dst, (size_t)n * 16));
+  MCB_CUDA(cudaMalloc(&daos, (size_t)n * 24));
+  const mcb::JumpTable jt = mcb::make_jump_table(mcb::kSeedG, mcb::kSeedC);
+  volatile float cell = x_ini / dx;
+  MCB_CUDA(mcb::launch_birth(n, seed, jt, x_ini, wmc, (int)cell, ds, dst, nullptr));
+  MCB_CUDA(mcb::launch_soa_to_aos(n, ds, dst, daos, nullptr));
+  MCB_CUDA(cudaMemcpy(out_host, daos, (size_t)n * 24, cudaMemcpyDeviceToHost));
+  cudaFree(ds);
+  cudaFree(dst);
+  cudaFree(daos);
+  return MCB200_OK;
+}
+
+}  // extern "C"
