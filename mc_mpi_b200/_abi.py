@@ -1,0 +1,117 @@
+"""ctypes binding of include/mcb200.h (libmcb200.so).
+
+The product path has no CPU fallback: if the CUDA library is missing or was
+not built, importing the binding raises -- loudly -- instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcb200.so")
+
+ABI_VERSION = 1
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_RANGE = 0, -1, -2, -3, -4, -5
+
+# include/types/particle.hpp:7-18 -- 24-byte wire format
+PARTICLE_DTYPE = np.dtype(
+    [("seed", "<u8"), ("x", "<f4"), ("mu", "<f4"), ("wmc", "<f4"), ("index", "<i4")]
+)
+assert PARTICLE_DTYPE.itemsize == 24
+
+
+class McbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mcb200 error {code}: {msg}")
+        self.code = code
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("x_min", C.c_float), ("x_max", C.c_float),
+        ("index_start", C.c_int32), ("m", C.c_int32),
+        ("dx", C.c_float), ("particle_min_weight", C.c_float),
+        ("left_border", C.c_int32), ("right_border", C.c_int32),
+        ("sigs", C.c_void_p), ("absorption_rates", C.c_void_p),
+        ("wmc_max", C.c_float), ("keep_border", C.c_int32),
+    ]
+
+
+class Counts(C.Structure):
+    _fields_ = [
+        ("nb_disabled", C.c_int64), ("nb_active", C.c_int64), ("n_bank", C.c_int64),
+        ("n_unborn", C.c_int64), ("n_outbox_left", C.c_int64), ("n_outbox_right", C.c_int64),
+        ("events", C.c_int64), ("scatters", C.c_int64), ("n_left", C.c_int64),
+        ("n_right", C.c_int64), ("n_dead", C.c_int64), ("w_left", C.c_double),
+        ("w_right", C.c_double), ("w_dead", C.c_double), ("launches", C.c_int64),
+        ("track_ms", C.c_double), ("gpu_launches", C.c_int64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/mcb200.h declares: name -> (restype, argtypes)
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SYMBOLS = {
+    "mcb200_layer_create": (C.c_int, [C.POINTER(LayerDesc), C.POINTER(_P)]),
+    "mcb200_layer_destroy": (None, [_P]),
+    "mcb200_layer_clone": (C.c_int, [_P, C.POINTER(_P)]),
+    "mcb200_layer_set_cross_sections": (C.c_int, [_P, _P, _P]),
+    "mcb200_layer_get_cross_sections": (C.c_int, [_P, _P, _P]),
+    "mcb200_layer_create_particles": (C.c_int, [_P, _F, _F, _I64, C.c_uint64]),
+    "mcb200_layer_push": (C.c_int, [_P, _P, _I64]),
+    "mcb200_layer_push_device": (C.c_int, [_P, _P, _I64]),
+    "mcb200_layer_simulate": (C.c_int, [_P, _I64, C.POINTER(Counts)]),
+    "mcb200_layer_counts": (C.c_int, [_P, C.POINTER(Counts)]),
+    "mcb200_layer_pop_left": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
+    "mcb200_layer_pop_right": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
+    "mcb200_layer_pop_left_device": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
+    "mcb200_layer_pop_right_device": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
+    "mcb200_layer_weights_absorbed": (C.c_int, [_P, _P]),
+    "mcb200_layer_weights_absorbed_f64": (C.c_int, [_P, _P]),
+    "mcb200_layer_weights_absorbed_q": (C.c_int, [_P, _P, C.POINTER(_I32)]),
+    "mcb200_layer_dump_WA": (C.c_int, [_P, C.c_char_p]),
+    "mcb200_layer_stream": (_P, [_P]),
+    "mcb200_layer_set_option": (C.c_int, [_P, C.c_char_p, _I64]),
+    "mcb200_last_error": (C.c_char_p, []),
+    "mcb200_abi_version": (C.c_int, []),
+    "mcb200_device_count": (C.c_int, []),
+    "mcb200_test_rnd_real": (C.c_int, [C.c_int, _P, _P, _I64]),
+    "mcb200_test_logf": (C.c_int, [C.c_int, _P, _P, _I64]),
+    "mcb200_test_expf": (C.c_int, [C.c_int, _P, _P, _I64]),
+    "mcb200_test_birth": (C.c_int, [C.c_int, _F, _F, _F, _I64, C.c_uint64, _P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded libmcb200.so; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m mc_mpi_b200.build` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError = header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        if L.mcb200_abi_version() != ABI_VERSION:
+            raise ImportError("libmcb200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise McbError(rc, lib().mcb200_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return lib().mcb200_device_count()
