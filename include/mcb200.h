@@ -30,7 +30,7 @@ enum {
   MCB200_ERR_CUDA = -2,     /* CUDA runtime error (message has the string) */
   MCB200_ERR_NOMEM = -3,    /* host or device allocation failed */
   MCB200_ERR_CAPACITY = -4, /* caller buffer too small */
-  MCB200_ERR_RANGE = -5     /* particle weight above the layer's wmc_max */
+  MCB200_ERR_RANGE = -5     /* a weight / deposit outside (-2^7, 2^7): not a Monte-Carlo weight */
 };
 
 /* include/types/particle.hpp:7-18 -- the 24-byte POD the workers ship over
@@ -60,10 +60,6 @@ typedef struct mcb200_layer_desc {
   int32_t right_border;       /* 1/0, or -1 -> |x_max - 1| < 1e-4  (layer.cpp:48) */
   const float *sigs;              /* m floats, or NULL -> expf(-x_mid) (layer.cpp:53-60) */
   const float *absorption_rates;  /* m floats, or NULL -> 0.5       (layer.cpp:63) */
-  float wmc_max;              /* upper bound of any particle weight this layer
-                                 will ever see (1/nb_particles for a reference
-                                 run).  Sets the fixed-point tally unit:
-                                 2^-k with wmc_max * 2^k in [2^29, 2^30). */
   int32_t keep_border;        /* 1: particles absorbed at a global border are
                                  ALSO written to the outboxes (tests); 0: only
                                  counted, like layer.cpp:350-360 */
@@ -142,13 +138,16 @@ int mcb200_layer_pop_left_device(mcb200_layer *l, void *dev_aos, int64_t cap,
                                  int64_t *n_out);
 int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap,
                                   int64_t *n_out);
-/* weights_absorbed (layer.hpp:92), m entries.  _f32 is what the reference
- * exposes; _f64 and _q are the same tally without the float rounding:
- * tally = q * 2^-log2_scale exactly. */
+/* weights_absorbed (layer.hpp:92), m entries.  The device keeps every cell as
+ * an EXACT 128-bit fixed-point sum of the per-event float deposits (order-,
+ * launch- and GPU-count-independent).  _exact returns it: four little-endian
+ * 32-bit digits per cell, out[4*c + j], two's complement, value = integer *
+ * 2^lsb_log2 (lsb_log2 = -120).  _f64 / the float version the reference
+ * exposes are that number rounded once. */
 int mcb200_layer_weights_absorbed(mcb200_layer *l, float *out_m);
 int mcb200_layer_weights_absorbed_f64(mcb200_layer *l, double *out_m);
-int mcb200_layer_weights_absorbed_q(mcb200_layer *l, int64_t *out_m,
-                                    int32_t *log2_scale);
+int mcb200_layer_weights_absorbed_exact(mcb200_layer *l, uint32_t *out_4m,
+                                        int32_t *lsb_log2);
 /* Layer::dump_WA(), src/layer.cpp:363-380, same "%.4e %.3e\n" text; path NULL
  * -> "WA.out" in the current directory like the reference */
 int mcb200_layer_dump_WA(mcb200_layer *l, const char *path);
@@ -158,8 +157,7 @@ int mcb200_layer_dump_WA(mcb200_layer *l, const char *path);
  * timing by the caller) */
 void *mcb200_layer_stream(mcb200_layer *l);
 /* tuning knobs; key/value, returns MCB200_ERR_INVALID for unknown keys:
- *   "tally_mode"   0 auto, 1 shared-memory tally, 2 global (L2) tally
- *   "warp_agg"     0/1 warp-aggregated tally atomics (match.any + redux)
+ *   "tally_mode"   0 auto, 1 CTA-private shared-memory tally, 2 global (L2) tally
  *   "block"        threads per CTA,  "blocks_per_sm" CTAs per SM
  *   "birth_chunk"  max particles born per launch */
 int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value);
@@ -176,6 +174,9 @@ int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host,
 /* device logf / expf as used by the tracking kernel, element-wise */
 int mcb200_test_logf(int device, const float *in_host, float *out_host, int64_t n);
 int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t n);
+/* the exact accumulator the tally uses: sum of n floats -> 4 digits (+ rounded double) */
+int mcb200_test_accumulate(int device, const float *in_host, int64_t n,
+                           uint32_t *out4, double *out_f64);
 /* device-side birth only: first n particles of create_particles(x_ini,wmc,.,seed) */
 int mcb200_test_birth(int device, float x_ini, float wmc, float dx, int64_t n,
                       uint64_t seed, mcb200_particle *out_host);

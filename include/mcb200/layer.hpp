@@ -91,9 +91,6 @@ public:
   int nb_particles_create = 0;
 
   // -- extensions (not in the reference) --
-  // bound on any particle weight this layer will see; decompose_domain sets
-  // 1/nb_particles.  Must be set before the first simulate().
-  void set_wmc_max(real_t w);
   // cell width used for the edges; decompose_domain_global_dx passes the ONE
   // global dx so that K layers reproduce the single-layer trajectories
   void set_edge_dx(real_t w);
@@ -105,7 +102,6 @@ private:
   void ensure_device();
   void sync_cross_sections();
   mcb200_layer *h_ = nullptr;
-  real_t wmc_max_ = 0;
   real_t edge_dx_ = 0;
   std::vector<real_t> sigs_uploaded_, abs_uploaded_;
 };

@@ -37,7 +37,7 @@ class LayerDesc(C.Structure):
         ("dx", C.c_float), ("particle_min_weight", C.c_float),
         ("left_border", C.c_int32), ("right_border", C.c_int32),
         ("sigs", C.c_void_p), ("absorption_rates", C.c_void_p),
-        ("wmc_max", C.c_float), ("keep_border", C.c_int32),
+        ("keep_border", C.c_int32),
     ]
 
 
@@ -74,7 +74,7 @@ SYMBOLS = {
     "mcb200_layer_pop_right_device": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
     "mcb200_layer_weights_absorbed": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_f64": (C.c_int, [_P, _P]),
-    "mcb200_layer_weights_absorbed_q": (C.c_int, [_P, _P, C.POINTER(_I32)]),
+    "mcb200_layer_weights_absorbed_exact": (C.c_int, [_P, _P, C.POINTER(_I32)]),
     "mcb200_layer_dump_WA": (C.c_int, [_P, C.c_char_p]),
     "mcb200_layer_stream": (_P, [_P]),
     "mcb200_layer_set_option": (C.c_int, [_P, C.c_char_p, _I64]),
@@ -84,6 +84,7 @@ SYMBOLS = {
     "mcb200_test_rnd_real": (C.c_int, [C.c_int, _P, _P, _I64]),
     "mcb200_test_logf": (C.c_int, [C.c_int, _P, _P, _I64]),
     "mcb200_test_expf": (C.c_int, [C.c_int, _P, _P, _I64]),
+    "mcb200_test_accumulate": (C.c_int, [C.c_int, _P, _I64, _P, C.POINTER(C.c_double)]),
     "mcb200_test_birth": (C.c_int, [C.c_int, _F, _F, _F, _I64, C.c_uint64, _P]),
 }
 

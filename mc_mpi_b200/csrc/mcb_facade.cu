@@ -59,7 +59,7 @@ Layer::Layer(const Layer &o)
       nb_disabled(o.nb_disabled), left_border(o.left_border), right_border(o.right_border),
       sigs(o.sigs), absorption_rates(o.absorption_rates),
       particle_min_weight(o.particle_min_weight), seed(o.seed), x_ini(o.x_ini), wmc(o.wmc),
-      nb_particles_create(o.nb_particles_create), wmc_max_(o.wmc_max_), edge_dx_(o.edge_dx_),
+      nb_particles_create(o.nb_particles_create), edge_dx_(o.edge_dx_),
       sigs_uploaded_(o.sigs_uploaded_), abs_uploaded_(o.abs_uploaded_) {
   if (o.h_) die_on(mcb200_layer_clone(o.h_, &h_), "Layer copy");
 }
@@ -72,7 +72,7 @@ Layer::Layer(Layer &&o) noexcept
       right_border(o.right_border), sigs(std::move(o.sigs)),
       absorption_rates(std::move(o.absorption_rates)),
       particle_min_weight(o.particle_min_weight), seed(o.seed), x_ini(o.x_ini), wmc(o.wmc),
-      nb_particles_create(o.nb_particles_create), h_(o.h_), wmc_max_(o.wmc_max_),
+      nb_particles_create(o.nb_particles_create), h_(o.h_),
       edge_dx_(o.edge_dx_), sigs_uploaded_(std::move(o.sigs_uploaded_)),
       abs_uploaded_(std::move(o.abs_uploaded_)) {
   o.h_ = nullptr;
@@ -80,14 +80,6 @@ Layer::Layer(Layer &&o) noexcept
 
 Layer::~Layer() {
   if (h_) mcb200_layer_destroy(h_);
-}
-
-void Layer::set_wmc_max(real_t w) {
-  if (h_) {
-    std::fprintf(stderr, "mcb200: set_wmc_max after the device layer exists\n");
-    std::exit(EXIT_FAILURE);
-  }
-  wmc_max_ = w;
 }
 
 void Layer::set_edge_dx(real_t w) {
@@ -114,12 +106,6 @@ void Layer::ensure_device() {
   d.right_border = right_border;
   d.sigs = sigs.data();
   d.absorption_rates = absorption_rates.data();
-  real_t wm = wmc_max_;
-  if (!(wm > 0)) wm = wmc;  // a source layer knows its particle weight
-  for (const Particle &p : particles)
-    if (p.wmc > wm) wm = p.wmc;
-  if (!(wm > 0)) wm = 1.0f;
-  d.wmc_max = wm;
   d.keep_border = 0;
   die_on(mcb200_layer_create(&d, &h_), "Layer (device side)");
   sigs_uploaded_ = sigs;
@@ -241,7 +227,6 @@ static Layer decompose_impl(real_t x_min, real_t x_max, real_t x_ini, int world_
 
   Layer layer(x_min + start_index * dx, x_min + (start_index + nb_my_cells) * dx, start_index,
               nb_my_cells, particle_min_weight);
-  layer.set_wmc_max((real_t)(1.0 / nb_particles));
   if (global_dx) layer.set_edge_dx(dx);
   if ((cell_ini >= start_index) && (cell_ini < start_index + nb_my_cells)) {
     seed_t seed = 5127801;  // :36
@@ -283,10 +268,6 @@ void cusimulate(int n, Particle *particles, float const *const sigs,
   d.right_border = 0;            // who does the border bookkeeping (layer.cpp:264-298)
   d.sigs = sigs;
   d.absorption_rates = absorption_rates;
-  float wm = 0.0f;
-  for (int i = 0; i < n; ++i)
-    if (particles[i].wmc > wm) wm = particles[i].wmc;
-  d.wmc_max = wm > 0.0f ? wm : 1.0f;
   mcb200_layer *h = nullptr;
   die_on(mcb200_layer_create(&d, &h), "cusimulate: layer");
   die_on(mcb200_layer_push(h, reinterpret_cast<const mcb200_particle *>(particles), n),

@@ -1,6 +1,6 @@
 // mcb_kernels.cu -- hand-written sm_100a kernels of the particle-tracking path.
 //
-// track_kernel<SHARED, AGG> is the product: a persistent, history-based
+// track_kernel<SHARED> is the product: a persistent, history-based
 // tracking kernel.  Each lane owns one particle in registers and runs the
 // reference's event loop (src/layer.cpp:123-218) until the particle leaves the
 // sub-slab or drops below particle_min_weight; finished lanes are retired and
@@ -9,9 +9,9 @@
 // default slab).  Per event:
 //    * 1-2 steps of the per-particle 64-bit LCG (registers only),
 //    * glibc-exact logf / expf in FP64, two IEEE fp32 divides,
-//    * one fixed-point deposit into the CTA-private per-cell tally in shared
-//      memory (native 32-bit ATOMS.ADD + rare carry; optionally aggregated per
-//      warp with match.any + redux), flushed ONCE per CTA with 64-bit REDs,
+//    * one EXACT deposit into the CTA-private per-cell tally in shared memory
+//      (128-bit long accumulator in 32-bit digits: 1-2 native ATOMS.ADD plus
+//      rare carries), merged into the global tally ONCE per CTA,
 //    * escapees compacted with ballot/popc prefix sums into contiguous
 //      left / right outboxes (one global atomic per warp per retire event).
 // Nothing on this path is a contraction: no tensor cores by design.
@@ -23,53 +23,90 @@ namespace mcb {
 
 // ---------------------------------------------------------------- helpers --
 
-// sum of a signed 32-bit value over the lanes of `mask`, exact in 64 bits.
-// Two 16-bit halves go through the integer REDUX unit (sums cannot overflow).
-__device__ __forceinline__ long long warp_sum_s32(unsigned mask, int v) {
-  const unsigned lo = __reduce_add_sync(mask, (unsigned)(v & 0xffff));
-  const int hi = __reduce_add_sync(mask, v >> 16);
-  return ((long long)hi << 16) + (long long)lo;
+// Exact deposit of one float into a 128-bit accumulator (see mcb_kernels.cuh):
+// the 24-bit significand goes to bit position (exponent - 30) of a little-endian
+// number held in four 32-bit digits `w[0], w[stride], w[2*stride], w[3*stride]`.
+// Common case: one native 32-bit atomic add (ATOMS.ADD / ATOMG.ADD) when the
+// significand sits inside one digit, two when it straddles; carries ripple by
+// further adds only when a digit wraps.  The final digits do not depend on the
+// interleaving: every step is an exact add modulo 2^128.
+__device__ __forceinline__ void acc_add(unsigned *w, int stride, float v, unsigned *range_flag) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned e = (b >> 23) & 0xffu;
+  unsigned mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
+  int pos = (int)(e ? e : 1u) - (150 + kAccLsbLog2);   // bit position of the significand's LSB
+  if (pos < 0) {                                        // below 2^-97: drop the bits under the LSB
+    mant = pos > -24 ? mant >> (-pos) : 0u;
+    pos = 0;
+  }
+  if (mant == 0u) return;
+  if (pos > 32 * kAccDigits - 25) {                     // |v| >= 2^8 (or inf / nan): not a weight
+    atomicExch(range_flag, 1u);
+    return;
+  }
+  int j = pos >> 5;
+  const int o = pos & 31;
+  const unsigned lo = mant << o;
+  const unsigned hi = __funnelshift_l(mant, 0u, o);     // bits pushed into the next digit
+  if ((int)b >= 0) {
+    unsigned old = atomicAdd(&w[j * stride], lo);
+    unsigned c = hi + (old > ~lo ? 1u : 0u);
+    while (c != 0u && ++j < kAccDigits) {
+      old = atomicAdd(&w[j * stride], c);
+      c = old > ~c ? 1u : 0u;
+    }
+  } else {                                              // negative deposit: exact subtract
+    unsigned old = atomicSub(&w[j * stride], lo);
+    unsigned c = hi + (old < lo ? 1u : 0u);
+    while (c != 0u && ++j < kAccDigits) {
+      old = atomicSub(&w[j * stride], c);
+      c = old < c ? 1u : 0u;
+    }
+  }
 }
 
-// 64-bit add into a {lo, hi} pair of 32-bit shared-memory words.  The common
-// case is ONE native ATOMS.ADD (shared 64-bit and float atomics are CAS loops
-// on sm_100a); the carry / sign word is touched only when it changes.
-__device__ __forceinline__ void smem_add64(unsigned *lo, unsigned *hi, int il,
-                                           long long v) {
-  const unsigned uq = (unsigned)v;
-  const unsigned old = atomicAdd(&lo[il], uq);
-  const unsigned h = (unsigned)(v >> 32) + (old > ~uq ? 1u : 0u);
-  if (h) atomicAdd(&hi[il], h);
+// add a whole accumulator (digits d[0..3] of one cell) into another one
+__device__ __forceinline__ void acc_merge(unsigned *w, int stride, const unsigned d[kAccDigits]) {
+  unsigned c = 0u;
+#pragma unroll
+  for (int j = 0; j < kAccDigits; ++j) {
+    // digit + incoming carry, as up to two adds so that neither can exceed 32 bits
+    unsigned carry_out = 0u;
+    if (d[j]) {
+      const unsigned old = atomicAdd(&w[j * stride], d[j]);
+      carry_out += old > ~d[j] ? 1u : 0u;
+    }
+    if (c) {
+      const unsigned old = atomicAdd(&w[j * stride], c);
+      carry_out += old > ~c ? 1u : 0u;
+    }
+    c = carry_out;
+  }
 }
 
 struct TrackSmem {
   MathTables math;
-  unsigned long long w_cls[3];
   unsigned int n_cls[3];
   unsigned int pad;
 };
 
 // ----------------------------------------------------------- the hot path --
 
-template <bool SHARED, bool AGG>
+template <bool SHARED>
 __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem *sm = reinterpret_cast<TrackSmem *>(smem_raw);
   CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(TrackSmem));
-  unsigned *s_lo = reinterpret_cast<unsigned *>(s_xs + (SHARED ? p.m : 0));
-  unsigned *s_hi = s_lo + (SHARED ? p.m : 0);
+  const int ncell = p.m + kAccExtra;
+  // CTA-private copy of the tally (digit-major) when it fits in shared memory,
+  // else the L2-resident global one
+  unsigned *acc = SHARED ? reinterpret_cast<unsigned *>(s_xs + p.m) : p.acc;
 
   load_math_tables(&sm->math);
-  if (threadIdx.x < 3) {
-    sm->w_cls[threadIdx.x] = 0ull;
-    sm->n_cls[threadIdx.x] = 0u;
-  }
+  if (threadIdx.x < 3) sm->n_cls[threadIdx.x] = 0u;
   if (SHARED) {
-    for (int c = threadIdx.x; c < p.m; c += blockDim.x) {
-      s_xs[c] = p.xs[c];
-      s_lo[c] = 0u;
-      s_hi[c] = 0u;
-    }
+    for (int c = threadIdx.x; c < p.m; c += blockDim.x) s_xs[c] = p.xs[c];
+    for (int c = threadIdx.x; c < kAccDigits * ncell; c += blockDim.x) acc[c] = 0u;
   }
   __syncthreads();
 
@@ -77,7 +114,7 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
   const unsigned lt_mask = (1u << lane) - 1u;
   const int lo = p.idx_lo;
   const int hi = p.idx_lo + p.m;
-  const float dx = p.dx, minw = p.minw, qscale = p.qscale;
+  const float dx = p.dx, minw = p.minw;
   const unsigned long long take = (unsigned long long)p.take_count;
 
   // particle state, include/types/particle.hpp:7-18, one history per lane
@@ -97,7 +134,7 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
       // ---- retire: classification of src/layer.cpp:202-217, routing of
       // :332-346, global-border absorption of :350-360
       const int cls = (idx == lo - 1) ? 0 : (idx == hi) ? 1 : (wmc < minw) ? 2 : 0;
-      const int wq = __float2int_rn(__fmul_rn(wmc, qscale));
+      if (fin) acc_add(&acc[p.m + cls], ncell, wmc, &p.ctr->acc_range);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const bool mine = fin && cls == c;
@@ -105,12 +142,7 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
         if (cm == 0u) continue;
         const int cnt = __popc(cm);
         const int leader = __ffs(cm) - 1;
-        long long wsum = 0;
-        if (mine) wsum = warp_sum_s32(cm, wq);
-        if (lane == leader) {
-          atomicAdd(&sm->n_cls[c], (unsigned)cnt);
-          atomicAdd(&sm->w_cls[c], (unsigned long long)wsum);
-        }
+        if (lane == leader) atomicAdd(&sm->n_cls[c], (unsigned)cnt);
         if (c < 2 && p.write_side[c]) {
           // warp-aggregated append: one reservation per warp, ranks by popc
           unsigned long long base = 0ull;
@@ -157,7 +189,6 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
     if (im == MCB_FULL) break;  // bank handed out and every lane retired
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
-    const unsigned am = __ballot_sync(MCB_FULL, alive);
     if (alive) {
       const int il = idx - lo;                                   // :129
       const CellXs xs = SHARED ? s_xs[il] : __ldg(&p.xs[il]);    // :131-133
@@ -185,25 +216,13 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
       const float e = expf_glibc_nonpos(__fmul_rn(-xs.x, di), &sm->math);
       const float dw = __fmul_rn(__fsub_rn(1.0f, e), wmc);       // :175
       wmc = __fsub_rn(wmc, dw);                                  // :178
-      // :179 weights_absorbed[il] += dw, as an exact fixed-point deposit
-      const int q = __float2int_rn(__fmul_rn(dw, qscale));
-      if (AGG) {
-        const unsigned peers = __match_any_sync(am, il);
-        const long long v = warp_sum_s32(peers, q);
-        if (lane == __ffs(peers) - 1) {
-          if (SHARED) smem_add64(s_lo, s_hi, il, v);
-          else atomicAdd(&p.tally_q[il], (unsigned long long)v);
-        }
-      } else {
-        if (SHARED) smem_add64(s_lo, s_hi, il, (long long)q);
-        else atomicAdd(&p.tally_q[il], (unsigned long long)(long long)q);
-      }
+      acc_add(&acc[il], ncell, dw, &p.ctr->acc_range);           // :179, exactly
       idx = inew;                                                // :181
       ++n_ev;
     }
   }
 
-  // ---- per-CTA flush: one 64-bit RED per touched cell, counters once
+  // ---- per-CTA flush: counters once, the CTA-private tally merged digit-wise
   unsigned long long ev = n_ev, sc = n_sc;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -216,34 +235,37 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
   }
   __syncthreads();
   if (SHARED) {
-    for (int c = threadIdx.x; c < p.m; c += blockDim.x) {
-      const unsigned long long v = ((unsigned long long)s_hi[c] << 32) | s_lo[c];
-      if (v) atomicAdd(&p.tally_q[c], v);
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+      unsigned d[kAccDigits];
+      unsigned any = 0u;
+#pragma unroll
+      for (int j = 0; j < kAccDigits; ++j) {
+        d[j] = acc[j * ncell + c];
+        any |= d[j];
+      }
+      if (any) acc_merge(&p.acc[c], ncell, d);
     }
   }
   if (threadIdx.x < 3) {
     const int c = threadIdx.x;
     if (sm->n_cls[c]) atomicAdd(&p.ctr->n_cls[c], (unsigned long long)sm->n_cls[c]);
-    if (sm->w_cls[c])
-      atomicAdd(reinterpret_cast<unsigned long long *>(&p.ctr->w_cls_q[c]), sm->w_cls[c]);
   }
 }
 
 size_t track_smem_bytes(int tally_mode, int m) {
   size_t b = sizeof(TrackSmem);
-  if (tally_mode == kTallyShared) b += (size_t)m * (sizeof(CellXs) + 2 * sizeof(unsigned));
+  if (tally_mode == kTallyShared)
+    b += (size_t)m * sizeof(CellXs) + (size_t)(m + kAccExtra) * kAccDigits * sizeof(unsigned);
   return b;
 }
 
 typedef void (*TrackFn)(const TrackParams);
-static TrackFn track_fn(int mode, int agg) {
-  if (mode == kTallyShared) return agg ? track_kernel<true, true> : track_kernel<true, false>;
-  return agg ? track_kernel<false, true> : track_kernel<false, false>;
+static TrackFn track_fn(int mode) {
+  return mode == kTallyShared ? track_kernel<true> : track_kernel<false>;
 }
 
-cudaError_t track_configure(int device, int m, int want_mode, int want_agg,
-                            int want_block, int want_blocks_per_sm,
-                            TrackLaunch *out) {
+cudaError_t track_configure(int device, int m, int want_mode, int want_block,
+                            int want_blocks_per_sm, TrackLaunch *out) {
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return e;
@@ -258,14 +280,14 @@ cudaError_t track_configure(int device, int m, int want_mode, int want_agg,
     return cudaErrorInvalidValue;
   const size_t smem = track_smem_bytes(mode, m);
 
-  // 1024 resident threads per SM (register budget of the kernel: 64/thread);
-  // CTA shape chosen so that the CTA-private tally copies fit
+  // CTA shape: as many resident threads as the register file allows, in CTAs
+  // small enough that their private tally copies fit side by side
   int block = want_block > 0 ? want_block : 256;
-  int bps = want_blocks_per_sm > 0 ? want_blocks_per_sm : 1024 / block;
+  int bps = want_blocks_per_sm > 0 ? want_blocks_per_sm : 1536 / block;
   if (want_block <= 0 && want_blocks_per_sm <= 0) {
     while (bps > 1 && (smem + reserve) * (size_t)bps > per_sm) {
       bps /= 2;
-      block *= 2;
+      if (block < 1024) block *= 2;
     }
   } else {
     while (bps > 1 && (smem + reserve) * (size_t)bps > per_sm) --bps;
@@ -273,19 +295,18 @@ cudaError_t track_configure(int device, int m, int want_mode, int want_agg,
   if (block > 1024 || block % 32) return cudaErrorInvalidValue;
 
   out->tally_mode = mode;
-  out->warp_agg = want_agg ? 1 : 0;
   out->block = block;
   out->grid = prop.multiProcessorCount * bps;
   out->smem = smem;
-  return cudaFuncSetAttribute(track_fn(mode, out->warp_agg),
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(track_fn(mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem);
 }
 
 cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStream_t stream) {
   if (p.take_count <= 0) return cudaSuccess;
   long long need = (p.take_count + cfg.block - 1) / cfg.block;
   int grid = (int)(need < (long long)cfg.grid ? need : (long long)cfg.grid);
-  track_fn(cfg.tally_mode, cfg.warp_agg)<<<grid, cfg.block, cfg.smem, stream>>>(p);
+  track_fn(cfg.tally_mode)<<<grid, cfg.block, cfg.smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -383,27 +404,6 @@ cudaError_t launch_soa_to_aos(long long n, const unsigned long long *seed, const
   return cudaGetLastError();
 }
 
-// max of wmc over n bank entries; weights are non-negative so the float bits
-// order like unsigned integers and a plain atomicMax on the bits works
-__global__ void __launch_bounds__(256) max_wmc_kernel(long long n, const float4 *__restrict__ st,
-                                                      unsigned *__restrict__ out_bits) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  float m = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    m = fmaxf(m, fabsf(st[i].z));
-  unsigned bits = __float_as_uint(m);
-  bits = __reduce_max_sync(MCB_FULL, bits);
-  if ((threadIdx.x & 31) == 0 && bits) atomicMax(out_bits, bits);
-}
-
-cudaError_t launch_max_wmc(long long n, const float4 *st, float *d_max_out, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(d_max_out, 0, sizeof(float), stream);
-  if (e != cudaSuccess || n <= 0) return e;
-  max_wmc_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(
-      n, st, reinterpret_cast<unsigned *>(d_max_out));
-  return cudaGetLastError();
-}
-
 // ---------------------------------------------------- known-answer kernels --
 
 // one rnd_real draw per element: the device counterpart of the reference's
@@ -437,6 +437,32 @@ cudaError_t launch_test_math(int which, long long n, const float *in, float *out
                              cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   test_math_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(which, n, in, out);
+  return cudaGetLastError();
+}
+
+// exact accumulation of n floats into one accumulator (test hook of acc_add):
+// a CTA-private copy in shared memory, merged like the tracking kernel does
+__global__ void test_accumulate_kernel(long long n, const float *in, unsigned *acc4,
+                                       unsigned *range_flag) {
+  __shared__ unsigned s_acc[kAccDigits];
+  if (threadIdx.x < kAccDigits) s_acc[threadIdx.x] = 0u;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc_add(s_acc, 1, in[i], range_flag);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned d[kAccDigits];
+    for (int j = 0; j < kAccDigits; ++j) d[j] = s_acc[j];
+    acc_merge(acc4, 1, d);
+  }
+}
+
+cudaError_t launch_test_accumulate(long long n, const float *in, unsigned *acc4,
+                                   cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  test_accumulate_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(n, in, acc4,
+                                                                 acc4 + kAccDigits);
   return cudaGetLastError();
 }
 

@@ -8,16 +8,32 @@
 
 namespace mcb {
 
+// ---- the tally: an exact long accumulator ---------------------------------
+// weights_absorbed[cell] (include/layer/layer.hpp:92) is kept per cell as a
+// 128-bit two's-complement fixed-point number, least significant bit 2^-120,
+// in four 32-bit digits.  A float deposit is its 24-bit significand shifted
+// to its exponent: an INTEGER add.  Integer adds are associative, so the
+// tally is the exact sum of the per-event floats (floats below 2^-97 lose the
+// bits under 2^-120) whatever the order, the CTA shape, the number of
+// launches or the number of GPUs -- unlike the reference's float tally, which
+// moves by 3e-4 per cell with the OpenMP thread count (SURVEY hard part 1).
+// The digits are 32-bit because sm_100a has native shared-memory atomics only
+// for 32-bit integers (64-bit and float shared atomics are CAS loops).
+constexpr int kAccDigits = 4;
+constexpr int kAccLsbLog2 = -120;
+// three extra "cells" after the m real ones collect the weight carried by
+// histories classified left / right / dead
+constexpr int kAccExtra = 3;
+
 // Device counters of one layer; zeroed per tracking launch, read back after.
 struct DevCounters {
   unsigned long long cursor;      // next unclaimed slot of the launch's bank range
   unsigned long long out_n[2];    // fill of the left / right outbox (persist across launches)
   unsigned long long n_cls[3];    // histories classified left / right / dead
-  long long w_cls_q[3];           // their weights, fixed point (unit 2^-k)
   unsigned long long events;
   unsigned long long scatters;
   unsigned int overflow;          // an outbox was too small (host sizes them so it cannot be)
-  unsigned int pad;
+  unsigned int acc_range;         // a deposit did not fit the accumulator (weight >= 2^8)
 };
 
 // per-cell constants of the event, precomputed once per layer from the public
@@ -39,9 +55,8 @@ struct TrackParams {
   int m;
   float dx;
   float minw;            // particle_min_weight
-  float qscale;          // 2^k, tally unit
   // outputs
-  unsigned long long *tally_q;  // m fixed-point accumulators (two's complement)
+  unsigned *acc;         // [kAccDigits][m + kAccExtra] digits, digit-major
   unsigned long long *out_seed[2];
   float4 *out_st[2];
   long long out_cap[2];
@@ -53,17 +68,14 @@ enum TallyMode { kTallyShared = 1, kTallyGlobal = 2 };
 
 struct TrackLaunch {
   int tally_mode;   // TallyMode
-  int warp_agg;     // 0/1
   int block;        // threads per CTA
   int grid;         // CTAs
   size_t smem;      // dynamic shared memory bytes
 };
 
-// largest m whose tables + tally fit in shared memory for the given CTA shape
 size_t track_smem_bytes(int tally_mode, int m);
-cudaError_t track_configure(int device, int m, int want_mode, int want_agg,
-                            int want_block, int want_blocks_per_sm,
-                            TrackLaunch *out);
+cudaError_t track_configure(int device, int m, int want_mode, int want_block,
+                            int want_blocks_per_sm, TrackLaunch *out);
 cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg,
                          cudaStream_t stream);
 
@@ -80,14 +92,14 @@ cudaError_t launch_aos_to_soa(long long n, const void *aos,
                               cudaStream_t stream);
 cudaError_t launch_soa_to_aos(long long n, const unsigned long long *seed,
                               const float4 *st, void *aos, cudaStream_t stream);
-// max wmc of n bank entries (range guard of the fixed-point tally)
-cudaError_t launch_max_wmc(long long n, const float4 *st, float *d_max_out,
-                           cudaStream_t stream);
 
 // known-answer-test kernels
 cudaError_t launch_test_rnd_real(long long n, unsigned long long *seeds,
                                  float *out, cudaStream_t stream);
 cudaError_t launch_test_math(int which, long long n, const float *in, float *out,
                              cudaStream_t stream);
+// exact accumulation of n floats into ONE accumulator (kAccDigits words)
+cudaError_t launch_test_accumulate(long long n, const float *in, unsigned *acc4,
+                                   cudaStream_t stream);
 
 }  // namespace mcb

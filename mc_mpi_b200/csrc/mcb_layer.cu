@@ -5,7 +5,8 @@
 //
 //   bank      seed[cap] (u64) + st[cap] (float4 {x, mu, wmc, bits(index)})
 //   outboxes  same layout, one per side, filled by the tracking kernel
-//   tally     u64[m] fixed point, unit 2^-k       xs  float2[m] {sig_a, sig_i}
+//   tally     u32[4][m+3] exact long accumulator (mcb_kernels.cuh)
+//   xs        float2[m] {sig_a, sig_i}
 //
 // Nothing here computes physics on the CPU: there is no fallback path.
 #include <cmath>
@@ -28,12 +29,12 @@ int fail(int code, const std::string &msg) {
   return code;
 }
 
-#define MCB_CUDA(expr)                                                              \
-  do {                                                                              \
-    cudaError_t e__ = (expr);                                                       \
-    if (e__ != cudaSuccess)                                                         \
+#define MCB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
       return fail(e__ == cudaErrorMemoryAllocation ? MCB200_ERR_NOMEM : MCB200_ERR_CUDA, \
-                  std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
   } while (0)
 
 struct DeviceGuard {
@@ -55,6 +56,14 @@ struct SoaBuf {
   long long cap = 0;
 };
 
+// 128-bit two's-complement accumulator (4 little-endian 32-bit digits, LSB
+// 2^kAccLsbLog2) -> double, rounded once
+double acc_to_double(const unsigned d[mcb::kAccDigits]) {
+  unsigned __int128 u = 0;
+  for (int j = mcb::kAccDigits - 1; j >= 0; --j) u = (u << 32) | d[j];
+  return std::ldexp((double)(__int128)u, mcb::kAccLsbLog2);
+}
+
 }  // namespace
 
 struct mcb200_layer {
@@ -72,9 +81,6 @@ struct mcb200_layer {
   unsigned long long chain_state = 0;
   float x_ini = 0, wmc = 0;
   long long n_unborn = 0;
-  // --- fixed-point tally
-  float wmc_max = 0;
-  int log2_scale = 0;
   // --- device state
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -83,23 +89,26 @@ struct mcb200_layer {
   SoaBuf outbox[2];
   long long n_out[2] = {0, 0};
   mcb::CellXs *d_xs = nullptr;
-  unsigned long long *d_tally = nullptr;
+  unsigned *d_acc = nullptr;          // [kAccDigits][m + kAccExtra]
   mcb::DevCounters *d_ctr = nullptr;
   mcb::DevCounters *h_ctr = nullptr;  // pinned
+  unsigned *h_cls = nullptr;          // pinned: digits of the 3 class accumulators
   void *d_stage = nullptr;            // AoS staging for push / pop
   long long stage_cap = 0;            // in particles
-  float *d_scalar = nullptr;
   bool xs_dirty = true;
   mcb::JumpTable seed_jump;
   // --- knobs / cumulative stats
-  int opt_tally_mode = 0, opt_warp_agg = 0, opt_block = 0, opt_bps = 0;
+  int opt_tally_mode = 0, opt_block = 0, opt_bps = 0;
   long long opt_birth_chunk = 1ll << 26;
   bool cfg_dirty = true;
   mcb::TrackLaunch cfg{};
   long long events = 0, scatters = 0, n_cls[3] = {0, 0, 0};
-  long long w_cls_q[3] = {0, 0, 0};
+  double w_cls[3] = {0, 0, 0};
   long long launches = 0, gpu_launches = 0;
   double track_ms = 0;
+
+  int ncell() const { return m + mcb::kAccExtra; }
+  size_t acc_words() const { return (size_t)mcb::kAccDigits * (size_t)ncell(); }
 };
 
 namespace {
@@ -143,15 +152,15 @@ int stage_reserve(mcb200_layer *l, long long n) {
   return MCB200_OK;
 }
 
-// per-cell event constants, src/layer.cpp:131-133 (host x86-64 code is built
-// without FMA contraction, like the reference)
+// per-cell event constants, src/layer.cpp:131-133 (host code is built with
+// -ffp-contract=off and no -mfma, like the reference: plain IEEE float ops)
 int upload_xs(mcb200_layer *l) {
   std::vector<mcb::CellXs> xs((size_t)l->m);
   for (int i = 0; i < l->m; ++i) {
     const float a = l->absorption_rates[(size_t)i];
     const float interaction_rate = (float)(1.0 - (double)a);
-    volatile float sig_a = l->sigs[(size_t)i] * a;
-    volatile float sig_i = l->sigs[(size_t)i] * interaction_rate;
+    const float sig_a = l->sigs[(size_t)i] * a;
+    const float sig_i = l->sigs[(size_t)i] * interaction_rate;
     xs[(size_t)i] = make_float2(sig_a, sig_i);
   }
   MCB_CUDA(cudaMemcpyAsync(l->d_xs, xs.data(), xs.size() * sizeof(mcb::CellXs),
@@ -161,12 +170,18 @@ int upload_xs(mcb200_layer *l) {
   return MCB200_OK;
 }
 
-int fetch_tally(mcb200_layer *l, std::vector<long long> *out) {
-  out->resize((size_t)l->m);
+// the m cell accumulators as cell-major digits: out[4*c + j]
+int fetch_tally(mcb200_layer *l, std::vector<unsigned> *out) {
   DeviceGuard g(l->device);
-  MCB_CUDA(cudaMemcpyAsync(out->data(), l->d_tally, (size_t)l->m * sizeof(long long),
+  std::vector<unsigned> raw(l->acc_words());
+  MCB_CUDA(cudaMemcpyAsync(raw.data(), l->d_acc, raw.size() * sizeof(unsigned),
                            cudaMemcpyDeviceToHost, l->stream));
   MCB_CUDA(cudaStreamSynchronize(l->stream));
+  out->resize((size_t)l->m * mcb::kAccDigits);
+  const size_t nc = (size_t)l->ncell();
+  for (int c = 0; c < l->m; ++c)
+    for (int j = 0; j < mcb::kAccDigits; ++j)
+      (*out)[(size_t)c * mcb::kAccDigits + j] = raw[(size_t)j * nc + (size_t)c];
   return MCB200_OK;
 }
 
@@ -175,7 +190,7 @@ int birth(mcb200_layer *l, long long n) {
   if (n <= 0) return MCB200_OK;
   int rc = soa_reserve(l, &l->bank, l->n_bank, l->n_bank + n);
   if (rc) return rc;
-  volatile float cell = l->x_ini / l->dx;  // :106, ignores x_min
+  const float cell = l->x_ini / l->dx;  // :106, ignores x_min
   const int index = (int)cell;
   MCB_CUDA(mcb::launch_birth(n, l->chain_state, l->seed_jump, l->x_ini, l->wmc, index,
                              l->bank.seed + l->n_bank, l->bank.st + l->n_bank, l->stream));
@@ -193,8 +208,8 @@ int track(mcb200_layer *l, long long take) {
     if (rc) return rc;
   }
   if (l->cfg_dirty) {
-    MCB_CUDA(mcb::track_configure(l->device, l->m, l->opt_tally_mode, l->opt_warp_agg,
-                                  l->opt_block, l->opt_bps, &l->cfg));
+    MCB_CUDA(mcb::track_configure(l->device, l->m, l->opt_tally_mode, l->opt_block, l->opt_bps,
+                                  &l->cfg));
     l->cfg_dirty = false;
   }
   const bool write_side[2] = {!l->left_border || l->keep_border,
@@ -220,8 +235,7 @@ int track(mcb200_layer *l, long long take) {
   p.m = l->m;
   p.dx = l->dx;
   p.minw = l->particle_min_weight;
-  p.qscale = std::ldexp(1.0f, l->log2_scale);
-  p.tally_q = l->d_tally;
+  p.acc = l->d_acc;
   for (int s = 0; s < 2; ++s) {
     p.out_seed[s] = l->outbox[s].seed;
     p.out_st[s] = l->outbox[s].st;
@@ -234,6 +248,11 @@ int track(mcb200_layer *l, long long take) {
   MCB_CUDA(cudaEventRecord(l->ev1, l->stream));
   MCB_CUDA(cudaMemcpyAsync(l->h_ctr, l->d_ctr, sizeof(mcb::DevCounters), cudaMemcpyDeviceToHost,
                            l->stream));
+  // digits of the three class accumulators (weight carried left / right / by the dead)
+  MCB_CUDA(cudaMemcpy2DAsync(l->h_cls, mcb::kAccExtra * sizeof(unsigned), l->d_acc + l->m,
+                             (size_t)l->ncell() * sizeof(unsigned),
+                             mcb::kAccExtra * sizeof(unsigned), mcb::kAccDigits,
+                             cudaMemcpyDeviceToHost, l->stream));
   MCB_CUDA(cudaStreamSynchronize(l->stream));
   float ms = 0.f;
   MCB_CUDA(cudaEventElapsedTime(&ms, l->ev0, l->ev1));
@@ -241,6 +260,8 @@ int track(mcb200_layer *l, long long take) {
   l->launches++;
   l->gpu_launches++;
   if (l->h_ctr->overflow) return fail(MCB200_ERR_CAPACITY, "internal: outbox overflow");
+  if (l->h_ctr->acc_range)
+    return fail(MCB200_ERR_RANGE, "a particle weight or deposit is outside (-2^7, 2^7)");
 
   const mcb::DevCounters &c = *l->h_ctr;
   l->n_bank -= take;
@@ -248,7 +269,9 @@ int track(mcb200_layer *l, long long take) {
   l->scatters += (long long)c.scatters;
   for (int k = 0; k < 3; ++k) {
     l->n_cls[k] += (long long)c.n_cls[k];
-    l->w_cls_q[k] += c.w_cls_q[k];
+    unsigned d[mcb::kAccDigits];
+    for (int j = 0; j < mcb::kAccDigits; ++j) d[j] = l->h_cls[j * mcb::kAccExtra + k];
+    l->w_cls[k] = acc_to_double(d);  // the device accumulators are cumulative
   }
   l->n_out[0] = (long long)c.out_n[0];
   l->n_out[1] = (long long)c.out_n[1];
@@ -261,7 +284,6 @@ int track(mcb200_layer *l, long long take) {
 
 int fill_counts(mcb200_layer *l, mcb200_counts *o) {
   if (!o) return MCB200_OK;
-  const double unit = std::ldexp(1.0, -l->log2_scale);
   o->nb_disabled = l->nb_disabled;
   o->nb_active = l->n_bank + l->n_unborn;
   o->n_bank = l->n_bank;
@@ -273,29 +295,12 @@ int fill_counts(mcb200_layer *l, mcb200_counts *o) {
   o->n_left = l->n_cls[0];
   o->n_right = l->n_cls[1];
   o->n_dead = l->n_cls[2];
-  o->w_left = (double)l->w_cls_q[0] * unit;
-  o->w_right = (double)l->w_cls_q[1] * unit;
-  o->w_dead = (double)l->w_cls_q[2] * unit;
+  o->w_left = l->w_cls[0];
+  o->w_right = l->w_cls[1];
+  o->w_dead = l->w_cls[2];
   o->launches = l->launches;
   o->track_ms = l->track_ms;
   o->gpu_launches = l->gpu_launches;
-  return MCB200_OK;
-}
-
-// range guard of the fixed-point tally: every weight must be <= wmc_max
-int check_wmc(mcb200_layer *l, long long first, long long n) {
-  if (n <= 0) return MCB200_OK;
-  MCB_CUDA(mcb::launch_max_wmc(n, l->bank.st + first, l->d_scalar, l->stream));
-  l->gpu_launches++;
-  float mx = 0.f;
-  MCB_CUDA(cudaMemcpyAsync(&mx, l->d_scalar, sizeof(float), cudaMemcpyDeviceToHost, l->stream));
-  MCB_CUDA(cudaStreamSynchronize(l->stream));
-  if (!(mx <= l->wmc_max)) {
-    char buf[160];
-    std::snprintf(buf, sizeof buf, "particle weight %.9g exceeds the layer's wmc_max %.9g", mx,
-                  l->wmc_max);
-    return fail(MCB200_ERR_RANGE, buf);
-  }
   return MCB200_OK;
 }
 
@@ -344,8 +349,8 @@ int push_any(mcb200_layer *l, const void *src, bool src_is_device, long long n) 
   MCB_CUDA(mcb::launch_aos_to_soa(n, aos, l->bank.seed + l->n_bank, l->bank.st + l->n_bank,
                                   l->stream));
   l->gpu_launches++;
-  rc = check_wmc(l, l->n_bank, n);
-  if (rc) return rc;
+  // the staging buffer / caller buffer may be reused as soon as we return
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
   l->n_bank += n;
   return MCB200_OK;
 }
@@ -371,8 +376,6 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   if (d->abi_version != MCB200_ABI_VERSION)
     return fail(MCB200_ERR_INVALID, "create: abi_version mismatch");
   if (d->m <= 0) return fail(MCB200_ERR_INVALID, "create: m must be positive");
-  if (!(d->wmc_max > 0.0f) || !std::isfinite(d->wmc_max))
-    return fail(MCB200_ERR_INVALID, "create: wmc_max must be a positive finite weight bound");
   int ndev = 0;
   MCB_CUDA(cudaGetDeviceCount(&ndev));
   if (d->device < 0 || d->device >= ndev)
@@ -385,10 +388,8 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   l->x_max = d->x_max;
   l->index_start = d->index_start;
   l->m = d->m;
-  {
-    volatile float w = (d->x_max - d->x_min) / d->m;  // src/layer.cpp:47
-    l->dx = d->dx > 0.0f ? d->dx : w;
-  }
+  const float ctor_dx = (d->x_max - d->x_min) / d->m;  // Layer::dx, src/layer.cpp:47
+  l->dx = d->dx > 0.0f ? d->dx : ctor_dx;
   l->particle_min_weight = d->particle_min_weight;
   l->left_border = d->left_border < 0 ? std::fabs((double)d->x_min) < (double)MCB_EPS
                                       : d->left_border != 0;
@@ -398,21 +399,11 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   l->sigs.resize((size_t)l->m);
   l->absorption_rates.resize((size_t)l->m);
   // cross-sections default to the reference's hard-coded ones (src/layer.cpp:53-63)
-  {
-    volatile float w = (d->x_max - d->x_min) / d->m;  // the ctor's own dx, :47
-    const float ldx = w;
-    for (int i = 0; i < l->m; ++i) {
-      volatile float base = d->x_min + (i * ldx);
-      const float x_mid = (float)((double)base + 0.5 * (double)ldx);  // :58
-      l->sigs[(size_t)i] = d->sigs ? d->sigs[i] : expf(-x_mid);        // :59
-      l->absorption_rates[(size_t)i] = d->absorption_rates ? d->absorption_rates[i] : 0.5f;
-    }
-  }
-  l->wmc_max = d->wmc_max;
-  {
-    int e = 0;
-    std::frexp(d->wmc_max, &e);  // wmc_max = f * 2^e, f in [0.5, 1)
-    l->log2_scale = 30 - e;      // wmc_max * 2^k in [2^29, 2^30)
+  for (int i = 0; i < l->m; ++i) {
+    const float base = d->x_min + (i * ctor_dx);
+    const float x_mid = (float)((double)base + 0.5 * (double)ctor_dx);  // :58
+    l->sigs[(size_t)i] = d->sigs ? d->sigs[i] : expf(-x_mid);            // :59
+    l->absorption_rates[(size_t)i] = d->absorption_rates ? d->absorption_rates[i] : 0.5f;
   }
   l->seed_jump = mcb::make_jump_table(mcb::kSeedG, mcb::kSeedC);
 
@@ -428,12 +419,13 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   cuda_ok(cudaEventCreate(&l->ev0), "cudaEventCreate");
   cuda_ok(cudaEventCreate(&l->ev1), "cudaEventCreate");
   cuda_ok(cudaMalloc(&l->d_xs, (size_t)l->m * sizeof(mcb::CellXs)), "cudaMalloc xs");
-  cuda_ok(cudaMalloc(&l->d_tally, (size_t)l->m * sizeof(unsigned long long)), "cudaMalloc tally");
+  cuda_ok(cudaMalloc(&l->d_acc, l->acc_words() * sizeof(unsigned)), "cudaMalloc tally");
   cuda_ok(cudaMalloc(&l->d_ctr, sizeof(mcb::DevCounters)), "cudaMalloc counters");
-  cuda_ok(cudaMalloc(&l->d_scalar, 16), "cudaMalloc scalar");
   cuda_ok(cudaMallocHost(&l->h_ctr, sizeof(mcb::DevCounters)), "cudaMallocHost counters");
+  cuda_ok(cudaMallocHost(&l->h_cls, mcb::kAccDigits * mcb::kAccExtra * sizeof(unsigned)),
+          "cudaMallocHost class weights");
   if (rc == MCB200_OK)
-    cuda_ok(cudaMemsetAsync(l->d_tally, 0, (size_t)l->m * sizeof(unsigned long long), l->stream),
+    cuda_ok(cudaMemsetAsync(l->d_acc, 0, l->acc_words() * sizeof(unsigned), l->stream),
             "cudaMemset tally");
   if (rc == MCB200_OK) cuda_ok(cudaStreamSynchronize(l->stream), "cudaStreamSynchronize");
   if (rc != MCB200_OK) {
@@ -458,11 +450,11 @@ void mcb200_layer_destroy(mcb200_layer *l) {
       cudaFree(l->outbox[s].st);
     }
     cudaFree(l->d_xs);
-    cudaFree(l->d_tally);
+    cudaFree(l->d_acc);
     cudaFree(l->d_ctr);
     cudaFree(l->d_stage);
-    cudaFree(l->d_scalar);
     if (l->h_ctr) cudaFreeHost(l->h_ctr);
+    if (l->h_cls) cudaFreeHost(l->h_cls);
     if (l->ev0) cudaEventDestroy(l->ev0);
     if (l->ev1) cudaEventDestroy(l->ev1);
     if (l->stream) cudaStreamDestroy(l->stream);
@@ -487,7 +479,6 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
   d.right_border = src->right_border;
   d.sigs = src->sigs.data();
   d.absorption_rates = src->absorption_rates.data();
-  d.wmc_max = src->wmc_max;
   d.keep_border = src->keep_border;
   mcb200_layer *l = nullptr;
   int rc = mcb200_layer_create(&d, &l);
@@ -513,8 +504,8 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
                         l->stream) != cudaSuccess)
       return bail(fail(MCB200_ERR_CUDA, "clone: device copy failed"));
   }
-  if (cudaMemcpyAsync(l->d_tally, src->d_tally, (size_t)l->m * 8, cudaMemcpyDeviceToDevice,
-                      l->stream) != cudaSuccess ||
+  if (cudaMemcpyAsync(l->d_acc, src->d_acc, l->acc_words() * sizeof(unsigned),
+                      cudaMemcpyDeviceToDevice, l->stream) != cudaSuccess ||
       cudaStreamSynchronize(l->stream) != cudaSuccess)
     return bail(fail(MCB200_ERR_CUDA, "clone: device copy failed"));
   l->n_bank = src->n_bank;
@@ -526,7 +517,6 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
   l->wmc = src->wmc;
   l->n_unborn = src->n_unborn;
   l->opt_tally_mode = src->opt_tally_mode;
-  l->opt_warp_agg = src->opt_warp_agg;
   l->opt_block = src->opt_block;
   l->opt_bps = src->opt_bps;
   l->opt_birth_chunk = src->opt_birth_chunk;
@@ -534,7 +524,7 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
   l->scatters = src->scatters;
   for (int k = 0; k < 3; ++k) {
     l->n_cls[k] = src->n_cls[k];
-    l->w_cls_q[k] = src->w_cls_q[k];
+    l->w_cls[k] = src->w_cls[k];
   }
   l->launches = src->launches;
   l->gpu_launches = src->gpu_launches;
@@ -564,8 +554,6 @@ int mcb200_layer_create_particles(mcb200_layer *l, float x_ini, float wmc, int64
                                   uint64_t seed) {
   if (!l || n < 0) return fail(MCB200_ERR_INVALID, "create_particles: bad argument");
   if (!(x_ini > l->x_min && x_ini < l->x_max)) return MCB200_OK;  // src/layer.cpp:73
-  if (!(wmc <= l->wmc_max) || wmc < 0.0f)
-    return fail(MCB200_ERR_RANGE, "create_particles: wmc outside [0, wmc_max]");
   l->x_ini = x_ini;  // :75-78
   l->wmc = wmc;
   l->n_unborn = n;
@@ -636,33 +624,32 @@ int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap, i
   return rc;
 }
 
-int mcb200_layer_weights_absorbed_q(mcb200_layer *l, int64_t *out_m, int32_t *log2_scale) {
-  if (!l || !out_m) return fail(MCB200_ERR_INVALID, "weights_absorbed_q: null argument");
-  std::vector<long long> q;
-  int rc = fetch_tally(l, &q);
+int mcb200_layer_weights_absorbed_exact(mcb200_layer *l, uint32_t *out_4m, int32_t *lsb_log2) {
+  if (!l || !out_4m) return fail(MCB200_ERR_INVALID, "weights_absorbed_exact: null argument");
+  std::vector<unsigned> d;
+  int rc = fetch_tally(l, &d);
   if (rc) return rc;
-  for (int i = 0; i < l->m; ++i) out_m[i] = q[(size_t)i];
-  if (log2_scale) *log2_scale = l->log2_scale;
+  std::memcpy(out_4m, d.data(), d.size() * sizeof(unsigned));
+  if (lsb_log2) *lsb_log2 = mcb::kAccLsbLog2;
   return MCB200_OK;
 }
 
 int mcb200_layer_weights_absorbed_f64(mcb200_layer *l, double *out_m) {
   if (!l || !out_m) return fail(MCB200_ERR_INVALID, "weights_absorbed_f64: null argument");
-  std::vector<long long> q;
-  int rc = fetch_tally(l, &q);
+  std::vector<unsigned> d;
+  int rc = fetch_tally(l, &d);
   if (rc) return rc;
-  const double unit = std::ldexp(1.0, -l->log2_scale);
-  for (int i = 0; i < l->m; ++i) out_m[i] = (double)q[(size_t)i] * unit;
+  for (int i = 0; i < l->m; ++i) out_m[i] = acc_to_double(&d[(size_t)i * mcb::kAccDigits]);
   return MCB200_OK;
 }
 
 int mcb200_layer_weights_absorbed(mcb200_layer *l, float *out_m) {
   if (!l || !out_m) return fail(MCB200_ERR_INVALID, "weights_absorbed: null argument");
-  std::vector<long long> q;
-  int rc = fetch_tally(l, &q);
+  std::vector<unsigned> d;
+  int rc = fetch_tally(l, &d);
   if (rc) return rc;
-  const double unit = std::ldexp(1.0, -l->log2_scale);
-  for (int i = 0; i < l->m; ++i) out_m[i] = (float)((double)q[(size_t)i] * unit);
+  for (int i = 0; i < l->m; ++i)
+    out_m[i] = (float)acc_to_double(&d[(size_t)i * mcb::kAccDigits]);
   return MCB200_OK;
 }
 
@@ -673,11 +660,10 @@ int mcb200_layer_dump_WA(mcb200_layer *l, const char *path) {
   if (rc) return rc;
   FILE *f = std::fopen(path ? path : "WA.out", "w");
   if (!f) return fail(MCB200_ERR_INVALID, "Couldn't open file WA.out for writing.");
-  volatile float wdx = (l->x_max - l->x_min) / l->m;  // the reference prints with Layer::dx
-  const float ldx = wdx;
-  for (int i = 0; i < l->m; ++i) {  // src/layer.cpp:373-377
-    volatile float base = l->x_min + (i * ldx);
-    volatile float ratio = w[(size_t)i] / ldx;
+  const float ldx = (l->x_max - l->x_min) / l->m;  // the reference prints with Layer::dx
+  for (int i = 0; i < l->m; ++i) {                 // src/layer.cpp:373-377
+    const float base = l->x_min + (i * ldx);
+    const float ratio = w[(size_t)i] / ldx;
     std::fprintf(f, "%.4e %.3e\n", (double)base + 0.5 * (double)ldx, (double)ratio);
   }
   std::fclose(f);
@@ -690,7 +676,6 @@ int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value) {
   if (!l || !key) return fail(MCB200_ERR_INVALID, "set_option: null argument");
   const std::string k(key);
   if (k == "tally_mode") l->opt_tally_mode = (int)value;
-  else if (k == "warp_agg") l->opt_warp_agg = (int)value;
   else if (k == "block") l->opt_block = (int)value;
   else if (k == "blocks_per_sm") l->opt_bps = (int)value;
   else if (k == "birth_chunk") {
@@ -746,6 +731,29 @@ int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t 
   return test_math(1, device, in_host, out_host, n);
 }
 
+int mcb200_test_accumulate(int device, const float *in_host, int64_t n, uint32_t *out4,
+                           double *out_f64) {
+  if (n < 0 || (n > 0 && !in_host) || !out4)
+    return fail(MCB200_ERR_INVALID, "test_accumulate: bad argument");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "test_accumulate: cudaSetDevice failed");
+  float *din = nullptr;
+  unsigned *dacc = nullptr;
+  MCB_CUDA(cudaMalloc(&din, (size_t)(n > 0 ? n : 1) * 4));
+  MCB_CUDA(cudaMalloc(&dacc, (mcb::kAccDigits + 1) * sizeof(unsigned)));
+  MCB_CUDA(cudaMemset(dacc, 0, (mcb::kAccDigits + 1) * sizeof(unsigned)));
+  if (n > 0) MCB_CUDA(cudaMemcpy(din, in_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_accumulate(n, din, dacc, nullptr));
+  unsigned h[mcb::kAccDigits + 1];
+  MCB_CUDA(cudaMemcpy(h, dacc, sizeof h, cudaMemcpyDeviceToHost));
+  cudaFree(din);
+  cudaFree(dacc);
+  for (int j = 0; j < mcb::kAccDigits; ++j) out4[j] = h[j];
+  if (out_f64) *out_f64 = acc_to_double(h);
+  if (h[mcb::kAccDigits]) return fail(MCB200_ERR_RANGE, "test_accumulate: value outside (-2^7, 2^7)");
+  return MCB200_OK;
+}
+
 int mcb200_test_birth(int device, float x_ini, float wmc, float dx, int64_t n, uint64_t seed,
                       mcb200_particle *out_host) {
   if (n < 0 || (n > 0 && !out_host)) return fail(MCB200_ERR_INVALID, "test_birth: bad argument");
@@ -759,7 +767,7 @@ int mcb200_test_birth(int device, float x_ini, float wmc, float dx, int64_t n, u
   MCB_CUDA(cudaMalloc(&dst, (size_t)n * 16));
   MCB_CUDA(cudaMalloc(&daos, (size_t)n * 24));
   const mcb::JumpTable jt = mcb::make_jump_table(mcb::kSeedG, mcb::kSeedC);
-  volatile float cell = x_ini / dx;
+  const float cell = x_ini / dx;
   MCB_CUDA(mcb::launch_birth(n, seed, jt, x_ini, wmc, (int)cell, ds, dst, nullptr));
   MCB_CUDA(mcb::launch_soa_to_aos(n, ds, dst, daos, nullptr));
   MCB_CUDA(cudaMemcpy(out_host, daos, (size_t)n * 24, cudaMemcpyDeviceToHost));

@@ -22,7 +22,7 @@ SEED0 = 5127801            # src/layer.cpp:36
 class Layer:
     """One sub-slab on one GPU (Layer::Layer, src/layer.cpp:44-69)."""
 
-    def __init__(self, x_min, x_max, index_start, m, particle_min_weight, *, wmc_max,
+    def __init__(self, x_min, x_max, index_start, m, particle_min_weight, *,
                  device=0, dx=None, sigs=None, absorption_rates=None, keep_border=False,
                  left_border=None, right_border=None):
         self._h = None
@@ -51,7 +51,6 @@ class Layer:
                     raise ValueError(f"{name} must have m={self.m} entries")
                 keep.append(a)
                 setattr(d, name, a.ctypes.data)
-        d.wmc_max = float(wmc_max)
         d.keep_border = int(bool(keep_border))
         h = C.c_void_p()
         check(_abi.lib().mcb200_layer_create(C.byref(d), C.byref(h)))
@@ -144,11 +143,13 @@ class Layer:
         check(_abi.lib().mcb200_layer_weights_absorbed_f64(self._h, out.ctypes.data))
         return out
 
-    def weights_absorbed_q(self):
-        """(int64[m], k): tally == q * 2**-k exactly."""
-        out = np.empty(self.m, dtype=np.int64)
+    def weights_absorbed_exact(self):
+        """(uint32[m, 4], lsb_log2): the exact tally, little-endian digits of a 128-bit
+        two's-complement integer per cell; tally == integer * 2**lsb_log2."""
+        out = np.empty((self.m, 4), dtype=np.uint32)
         k = C.c_int32(0)
-        check(_abi.lib().mcb200_layer_weights_absorbed_q(self._h, out.ctypes.data, C.byref(k)))
+        check(_abi.lib().mcb200_layer_weights_absorbed_exact(self._h, out.ctypes.data,
+                                                             C.byref(k)))
         return out, k.value
 
     def dump_WA(self, path="WA.out"):
@@ -210,7 +211,7 @@ def decompose_domain(x_min, x_max, x_ini, world_size, world_rank, nb_cells, nb_p
     hi = f32(x_min + f32(start_index + nb_my_cells) * dx)
     wmc = f32(1.0 / nb_particles)                                # :38, double -> float
     sl = slice(start_index, start_index + nb_my_cells)
-    layer = Layer(lo, hi, start_index, nb_my_cells, particle_min_weight, wmc_max=wmc,
+    layer = Layer(lo, hi, start_index, nb_my_cells, particle_min_weight,
                   device=device, dx=dx if global_dx else None, keep_border=keep_border,
                   sigs=None if sigs is None else np.asarray(sigs, dtype=np.float32)[sl],
                   absorption_rates=(None if absorption_rates is None
@@ -218,9 +219,3 @@ def decompose_domain(x_min, x_max, x_ini, world_size, world_rank, nb_cells, nb_p
     if start_index <= cell_ini < start_index + nb_my_cells:      # :34
         layer.create_particles(x_ini, wmc, nb_particles, seed)
     return layer
-
-
-def tally_log2_scale(wmc_max: float) -> int:
-    """k of the fixed-point tally unit 2^-k chosen by the library for wmc_max."""
-    _, e = math.frexp(float(f32(wmc_max)))
-    return 30 - e

@@ -88,8 +88,8 @@ struct orc_layer {
   int nb_particles_create;
   /* checker-side instrumentation */
   double *tally_f64;
-  int64_t *tally_q;
-  int log2_scale;
+  unsigned __int128 *tally_x; /* exact: integer * 2^ORC_ACC_LSB_LOG2, two's complement */
+  unsigned __int128 cls_x[3]; /* exact weight carried left / right / by the dead */
   int keep_border;
   pvec absorbed_left, absorbed_right, dead;
   orc_stats st;
@@ -111,8 +111,7 @@ orc_layer *orc_layer_new(float x_min, float x_max, int index_start, int m,
   l->absorption_rates = (float *)malloc(sizeof(float) * (size_t)(m > 0 ? m : 1));
   l->weights_absorbed = (float *)calloc((size_t)(m > 0 ? m : 1), sizeof(float));
   l->tally_f64 = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
-  l->tally_q = (int64_t *)calloc((size_t)(m > 0 ? m : 1), sizeof(int64_t));
-  l->log2_scale = 30;
+  l->tally_x = (unsigned __int128 *)calloc((size_t)(m > 0 ? m : 1), sizeof(unsigned __int128));
   for (int i = 0; i < m; ++i) {
     /* :58 -- (x_min + i*dx) in float, "+ 0.5*dx" in double, narrowed to float */
     float x_mid = (float)((double)(x_min + (i * l->dx)) + 0.5 * (double)l->dx);
@@ -129,7 +128,7 @@ void orc_layer_free(orc_layer *l) {
   free(l->absorption_rates);
   free(l->weights_absorbed);
   free(l->tally_f64);
-  free(l->tally_q);
+  free(l->tally_x);
   free(l->particles.d);
   free(l->particles_left.d);
   free(l->particles_right.d);
@@ -199,12 +198,37 @@ int orc_nb_active(const orc_layer *l) {
   return l->particles.n + l->nb_particles_create;
 }
 
+/*
+ * Exact accumulation (checker side of the CUDA path's long accumulator): a
+ * float is its 24-bit significand times a power of two, so with a fixed
+ * least significant bit of 2^ORC_ACC_LSB_LOG2 every deposit is an integer and
+ * the 128-bit two's-complement sum is exact and order-independent.  Bits below
+ * the LSB (floats under 2^-97) are dropped toward zero, like on the device.
+ */
+#define ORC_ACC_LSB_LOG2 (-120)
+static inline void acc_add_exact(unsigned __int128 *acc, float v) {
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  uint32_t e = (b >> 23) & 0xffu;
+  uint32_t mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
+  int pos = (int)(e ? e : 1u) - (150 + ORC_ACC_LSB_LOG2);
+  if (pos < 0) {
+    mant = pos > -24 ? mant >> (-pos) : 0u;
+    pos = 0;
+  }
+  if (mant == 0u || pos > 103) return; /* zero, or not a weight (>= 2^7, inf, nan) */
+  unsigned __int128 d = (unsigned __int128)mant << pos;
+  if (b >> 31) *acc -= d; else *acc += d;
+}
+static inline double acc_to_double(unsigned __int128 a) {
+  return ldexp((double)(__int128)a, ORC_ACC_LSB_LOG2);
+}
+
 /* accumulators one worker thread tallies into */
 typedef struct tally_ctx {
   float *wl;     /* thread-private float tally, like :314-315 */
   double *wd;
-  int64_t *wq;
-  float scale;   /* 2^log2_scale */
+  unsigned __int128 *wx;
   int64_t events, scatters;
 } tally_ctx;
 
@@ -250,7 +274,7 @@ static inline void particle_step(const orc_layer *l, orc_particle *p,
   p->wmc -= dw;                                      /* :178 */
   t->wl[il] += dw;                                   /* :179 */
   t->wd[il] += (double)dw;
-  t->wq[il] += (int64_t)(int32_t)lrintf(dw * t->scale);
+  acc_add_exact(&t->wx[il], dw);
   p->index = index_new;                              /* :181 */
   t->events++;
 }
@@ -301,7 +325,6 @@ static void simulate_impl(orc_layer *l, int nb_particles, int nthread) {
   int *result = (int *)malloc(sizeof(int) * (size_t)nb_particles);
   const int particles_size = l->particles.n;
   const int m = l->m;
-  const float scale = ldexpf(1.0f, l->log2_scale);
   int64_t ev = 0, sc = 0;
 
   if (nthread <= 1) {
@@ -309,8 +332,7 @@ static void simulate_impl(orc_layer *l, int nb_particles, int nthread) {
     tally_ctx t;
     t.wl = (float *)calloc((size_t)m, sizeof(float));
     t.wd = l->tally_f64;
-    t.wq = l->tally_q;
-    t.scale = scale;
+    t.wx = l->tally_x;
     t.events = t.scatters = 0;
     for (int i = 0; i < nb_particles; i++) /* :317-321, bank consumed backwards */
       result[i] = simulate_particle(l, &l->particles.d[particles_size - 1 - i], &t);
@@ -324,7 +346,8 @@ static void simulate_impl(orc_layer *l, int nb_particles, int nthread) {
 #endif
     float **wls = (float **)calloc((size_t)nthread, sizeof(float *));
     double **wds = (double **)calloc((size_t)nthread, sizeof(double *));
-    int64_t **wqs = (int64_t **)calloc((size_t)nthread, sizeof(int64_t *));
+    unsigned __int128 **wxs =
+        (unsigned __int128 **)calloc((size_t)nthread, sizeof(unsigned __int128 *));
     int64_t *evs = (int64_t *)calloc((size_t)nthread * 2, sizeof(int64_t));
     int used = 1;
 #pragma omp parallel
@@ -339,15 +362,14 @@ static void simulate_impl(orc_layer *l, int nb_particles, int nthread) {
       tally_ctx t;
       t.wl = (float *)calloc((size_t)m, sizeof(float));
       t.wd = (double *)calloc((size_t)m, sizeof(double));
-      t.wq = (int64_t *)calloc((size_t)m, sizeof(int64_t));
-      t.scale = scale;
+      t.wx = (unsigned __int128 *)calloc((size_t)m, sizeof(unsigned __int128));
       t.events = t.scatters = 0;
 #pragma omp for schedule(static)
       for (int i = 0; i < nb_particles; i++)
         result[i] = simulate_particle(l, &l->particles.d[particles_size - 1 - i], &t);
       wls[tid] = t.wl;
       wds[tid] = t.wd;
-      wqs[tid] = t.wq;
+      wxs[tid] = t.wx;
       evs[2 * tid] = t.events;
       evs[2 * tid + 1] = t.scatters;
     }
@@ -358,17 +380,17 @@ static void simulate_impl(orc_layer *l, int nb_particles, int nthread) {
       for (int j = 0; j < m; j++) {
         l->weights_absorbed[j] += wls[k][j];
         l->tally_f64[j] += wds[k][j];
-        l->tally_q[j] += wqs[k][j];
+        l->tally_x[j] += wxs[k][j];
       }
       ev += evs[2 * k];
       sc += evs[2 * k + 1];
       free(wls[k]);
       free(wds[k]);
-      free(wqs[k]);
+      free(wxs[k]);
     }
     free(wls);
     free(wds);
-    free(wqs);
+    free(wxs);
     free(evs);
   }
   l->st.events += ev;
@@ -381,16 +403,19 @@ static void simulate_impl(orc_layer *l, int nb_particles, int nthread) {
       pvec_push(&l->particles_left, p);
       l->st.n_left++;
       l->st.w_left += (double)p->wmc;
+      acc_add_exact(&l->cls_x[0], p->wmc);
       break;
     case 1:
       pvec_push(&l->particles_right, p);
       l->st.n_right++;
       l->st.w_right += (double)p->wmc;
+      acc_add_exact(&l->cls_x[1], p->wmc);
       break;
     case 0:
       l->nb_disabled++;
       l->st.n_dead++;
       l->st.w_dead += (double)p->wmc;
+      acc_add_exact(&l->cls_x[2], p->wmc);
       if (l->keep_border) pvec_push(&l->dead, p);
       break;
     }
@@ -461,10 +486,23 @@ int orc_particles_right_size(const orc_layer *l) { return l->particles_right.n; 
 orc_particle *orc_particles_right(orc_layer *l) { return l->particles_right.d; }
 void orc_clear_left(orc_layer *l) { l->particles_left.n = 0; }
 void orc_clear_right(orc_layer *l) { l->particles_right.n = 0; }
-void orc_set_tally_log2_scale(orc_layer *l, int k) { l->log2_scale = k; }
-int orc_tally_log2_scale(const orc_layer *l) { return l->log2_scale; }
 double *orc_tally_f64(orc_layer *l) { return l->tally_f64; }
-int64_t *orc_tally_q(orc_layer *l) { return l->tally_q; }
+void *orc_tally_exact(orc_layer *l) { return l->tally_x; }
+int orc_tally_exact_lsb_log2(void) { return ORC_ACC_LSB_LOG2; }
+void orc_tally_exact_f64(const orc_layer *l, double *out_m) {
+  for (int i = 0; i < l->m; i++) out_m[i] = acc_to_double(l->tally_x[i]);
+}
+/* exact class weights (left, right, dead) rounded once to double */
+void orc_class_weights_exact(const orc_layer *l, double out3[3]) {
+  for (int k = 0; k < 3; k++) out3[k] = acc_to_double(l->cls_x[k]);
+}
+/* exact sum of n floats: 16 bytes little-endian + the rounded double */
+double orc_accumulate_exact(const float *in, int64_t n, void *out16) {
+  unsigned __int128 a = 0;
+  for (int64_t i = 0; i < n; i++) acc_add_exact(&a, in[i]);
+  if (out16) memcpy(out16, &a, 16);
+  return acc_to_double(a);
+}
 void orc_set_keep_border(orc_layer *l, int keep) { l->keep_border = keep; }
 int orc_absorbed_left_size(const orc_layer *l) { return l->absorbed_left.n; }
 orc_particle *orc_absorbed_left(orc_layer *l) { return l->absorbed_left.d; }

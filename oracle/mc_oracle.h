@@ -92,18 +92,21 @@ void orc_clear_right(orc_layer *l);
 /*
  * Extra instrumentation the reference does not have (checker-side only).
  *  - double tally: the same per-event float dw summed in double.
- *  - fixed-point tally: q = (int32) rint(dw * 2^k) summed in int64; integer
- *    adds are associative, so this is what the CUDA path is compared to
- *    bit-for-bit.  k is set with orc_set_tally_log2_scale (default 30).
+ *  - exact tally: every float dw as an integer multiple of 2^-120, summed in
+ *    128-bit two's complement (unsigned __int128 per cell, 16 little-endian
+ *    bytes).  Integer adds are associative, so this is what the CUDA path's
+ *    long accumulator is compared to bit-for-bit.
  *  - "keep_border": when non-zero, particles escaping through a global border
  *    are ALSO appended to absorbed_left / absorbed_right before the reference
  *    semantics (count as disabled, drop) are applied, so tests can compare
  *    their final states.
  */
-void orc_set_tally_log2_scale(orc_layer *l, int k);
-int orc_tally_log2_scale(const orc_layer *l);
 double *orc_tally_f64(orc_layer *l);
-int64_t *orc_tally_q(orc_layer *l);
+void *orc_tally_exact(orc_layer *l);                 /* m x 16 bytes */
+int orc_tally_exact_lsb_log2(void);
+void orc_tally_exact_f64(const orc_layer *l, double *out_m);
+void orc_class_weights_exact(const orc_layer *l, double out3[3]);
+double orc_accumulate_exact(const float *in, int64_t n, void *out16);
 void orc_set_keep_border(orc_layer *l, int keep);
 int orc_absorbed_left_size(const orc_layer *l);
 orc_particle *orc_absorbed_left(orc_layer *l);

@@ -91,8 +91,10 @@ def oracle_lib():
             "orc_nb_active": (i, [P]),
             "orc_dump_WA": (i, [P, C.c_char_p]),
             "orc_push": (None, [P, P, i]),
-            "orc_set_tally_log2_scale": (None, [P, i]),
-            "orc_tally_log2_scale": (i, [P]),
+            "orc_tally_exact_lsb_log2": (i, []),
+            "orc_tally_exact_f64": (None, [P, P]),
+            "orc_class_weights_exact": (None, [P, P]),
+            "orc_accumulate_exact": (C.c_double, [P, C.c_int64, P]),
             "orc_set_keep_border": (None, [P, i]),
             "orc_get_stats": (None, [P, C.POINTER(_Stats)]),
             "orc_clear_left": (None, [P]),
@@ -112,7 +114,7 @@ def oracle_lib():
         for name in ("dx", "x_min", "x_max"):
             sig["orc_" + name] = (f, [P])
         for name in ("sigs", "absorption_rates", "weights_absorbed", "particles",
-                     "particles_left", "particles_right", "tally_f64", "tally_q",
+                     "particles_left", "particles_right", "tally_f64", "tally_exact",
                      "absorbed_left", "absorbed_right", "dead"):
             sig["orc_" + name] = (P, [P])
         for name, (res, args) in sig.items():
@@ -247,18 +249,26 @@ class OracleLayer(_LayerBase):
 
     index_start = property(lambda s: s._call("index_start"))
     tally_f64 = property(lambda s: _view(s._call("tally_f64"), s.m, "<f8"))
-    tally_q = property(lambda s: _view(s._call("tally_q"), s.m, "<i8"))
+    # exact tally as uint32[m, 4]: little-endian digits of the 128-bit sum per cell
+    tally_exact = property(lambda s: _view(s._call("tally_exact"), 4 * s.m, "<u4").reshape(-1, 4))
+
+    @property
+    def tally_exact_f64(self):
+        out = np.empty(self.m, dtype=np.float64)
+        self._lib.orc_tally_exact_f64(self._h, out.ctypes.data)
+        return out
+
+    @property
+    def class_weights_exact(self):
+        """exact weight carried left / right / by the dead, rounded once to double"""
+        out = np.empty(3, dtype=np.float64)
+        self._lib.orc_class_weights_exact(self._h, out.ctypes.data)
+        return out
     absorbed_left = property(
         lambda s: _view(s._call("absorbed_left"), s._call("absorbed_left_size"), PARTICLE_DTYPE))
     absorbed_right = property(
         lambda s: _view(s._call("absorbed_right"), s._call("absorbed_right_size"), PARTICLE_DTYPE))
     dead = property(lambda s: _view(s._call("dead"), s._call("dead_size"), PARTICLE_DTYPE))
-
-    def set_tally_log2_scale(self, k):
-        self._call("set_tally_log2_scale", k)
-
-    def tally_log2_scale(self):
-        return self._call("tally_log2_scale")
 
     def set_keep_border(self, keep=True):
         self._call("set_keep_border", int(keep))
@@ -351,3 +361,11 @@ def expf_v(x: np.ndarray, restated: bool) -> np.ndarray:
     out = np.empty_like(x)
     oracle_lib().orc_expf_v(int(restated), x.ctypes.data, out.ctypes.data, x.size)
     return out
+
+
+def accumulate_exact(x: np.ndarray):
+    """exact sum of floats: (uint32[4] little-endian digits, rounded double)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros(4, dtype=np.uint32)
+    d = oracle_lib().orc_accumulate_exact(x.ctypes.data, x.size, out.ctypes.data)
+    return out, d

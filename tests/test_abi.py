@@ -53,7 +53,7 @@ def test_struct_layouts_match_header(mcb_lib):
     int main(void){
       printf("%zu %zu %zu %zu %zu %zu\n", sizeof(mcb200_particle), sizeof(mcb200_layer_desc),
              sizeof(mcb200_counts), offsetof(mcb200_layer_desc, sigs),
-             offsetof(mcb200_layer_desc, wmc_max), offsetof(mcb200_counts, track_ms));
+             offsetof(mcb200_layer_desc, keep_border), offsetof(mcb200_counts, track_ms));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -65,7 +65,7 @@ def test_struct_layouts_match_header(mcb_lib):
         got = list(map(int, subprocess.run([exe], check=True, stdout=subprocess.PIPE,
                                            text=True).stdout.split()))
     want = [24, C.sizeof(_abi.LayerDesc), C.sizeof(_abi.Counts), _abi.LayerDesc.sigs.offset,
-            _abi.LayerDesc.wmc_max.offset, _abi.Counts.track_ms.offset]
+            _abi.LayerDesc.keep_border.offset, _abi.Counts.track_ms.offset]
     assert got == want
 
 
@@ -80,8 +80,8 @@ def test_argument_validation_without_compute(mcb_lib):
     d.m = 0
     assert mcb_lib.mcb200_layer_create(C.byref(d), C.byref(h)) == _abi.ERR_INVALID
     d.m = 10
-    d.wmc_max = 0.0
-    assert mcb_lib.mcb200_layer_create(C.byref(d), C.byref(h)) == _abi.ERR_INVALID
+    d.device = 10_000
+    assert mcb_lib.mcb200_layer_create(C.byref(d), C.byref(h)) in (_abi.ERR_INVALID, _abi.ERR_CUDA)
     assert mcb_lib.mcb200_layer_simulate(None, -1, None) == _abi.ERR_INVALID
     assert mcb_lib.mcb200_layer_push(None, None, 3) == _abi.ERR_INVALID
 
@@ -93,7 +93,7 @@ def test_no_cpu_fallback(mcb_lib):
         pytest.skip("a GPU is present; the no-device failure path cannot be exercised")
     from mc_mpi_b200.layer import Layer
     with pytest.raises(_abi.McbError) as ei:
-        Layer(0.0, 1.0, 0, 100, 0.0, wmc_max=0.01)
+        Layer(0.0, 1.0, 0, 100, 0.0)
     assert ei.value.code in (_abi.ERR_CUDA, _abi.ERR_INVALID)
     x = np.ones(4, dtype=np.float32)
     y = np.empty_like(x)

@@ -30,14 +30,17 @@ def assert_layer_matches_oracle(g: Layer, o, *, tol=1e-6):
     assert (c["n_left"], c["n_right"], c["n_dead"]) == (st["n_left"], st["n_right"], st["n_dead"])
     assert c["events"] == st["events"] and c["scatters"] == st["scatters"]
     assert c["nb_disabled"] == o.nb_disabled
-    # fixed-point tally: integer adds are associative -> bit-exact
-    q, k = g.weights_absorbed_q()
-    assert k == o.tally_log2_scale()
-    assert np.array_equal(q, o.tally_q)
+    # the tally is an exact integer sum on both sides -> all 128 bits of every cell agree
+    x, lsb = g.weights_absorbed_exact()
+    assert lsb == -120
+    assert np.array_equal(x, o.tally_exact)
     # and what the north star states: <= 1e-6 relative per cell vs the double tally
     t64 = o.tally_f64
     nz = t64 > 0
     assert np.max(np.abs(g.weights_absorbed_f64[nz] - t64[nz]) / t64[nz]) < tol
+    # weight carried out / left in the dead: exact sums too
+    cw = o.class_weights_exact
+    assert (c["w_left"], c["w_right"], c["w_dead"]) == (cw[0], cw[1], cw[2])
     # weight conservation
     injected = c["n_left"] + c["n_right"] + c["n_dead"]
     total = float(np.sum(g.weights_absorbed_f64)) + c["w_left"] + c["w_right"] + c["w_dead"]
@@ -101,15 +104,14 @@ def test_test_culayer_criterion(gpu):
         assert_layer_matches_oracle(g, o)
 
 
-@pytest.mark.parametrize("mode,agg", [(1, 0), (1, 1), (2, 0), (2, 1)])
-def test_tally_strategies_are_bit_identical(gpu, mode, agg):
-    """shared-memory vs L2 tally, with and without warp aggregation: same integers."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_tally_strategies_are_bit_identical(gpu, mode):
+    """CTA-private shared-memory tally vs global (L2) tally: same integers."""
     cfg = configs.reference_default(20_000)
     o = make_oracle(cfg)
     o.simulate(-1)
     with gpu_layer(cfg) as g:
         g.set_option("tally_mode", mode)
-        g.set_option("warp_agg", agg)
         g.simulate(-1)
         assert_layer_matches_oracle(g, o)
 
@@ -147,7 +149,7 @@ def test_partial_simulate_and_birth_chunks(gpu):
 def test_push_pop_roundtrip_and_edge_cases(gpu):
     cfg = configs.reference_default(1000)
     start, m = split_cells(cfg.nb_cells, 4, 1)
-    with Layer(0.25, 0.5, start, m, cfg.particle_min_weight, wmc_max=1e-3, keep_border=True,
+    with Layer(0.25, 0.5, start, m, cfg.particle_min_weight, keep_border=True,
                left_border=False, right_border=False) as g:
         # empty simulate is a no-op
         c = g.simulate(-1)
@@ -171,11 +173,13 @@ def test_push_pop_roundtrip_and_edge_cases(gpu):
         assert sorted(left["seed"].tolist()) == [11, 14]
         assert sorted(right["seed"].tolist()) == [12, 15]
         assert particles_equal(left, p[[0, 3]]) and particles_equal(right, p[[1, 4]])
-        # a weight above wmc_max is refused (fixed-point range guard)
+        # something that is not a Monte-Carlo weight (>= 2^7) is reported, not mis-tallied
         from mc_mpi_b200 import _abi
-        p["wmc"] = 1.0
+        p["wmc"] = 1000.0
+        p["index"] = start + 3
+        g.push(p)
         with pytest.raises(_abi.McbError) as ei:
-            g.push(p)
+            g.simulate(-1)
         assert ei.value.code == _abi.ERR_RANGE
 
 
@@ -191,10 +195,12 @@ def test_chain_of_layers_equals_reference_chain(gpu):
                             pop_left=lambda l: l.pop_left(), pop_right=lambda l: l.pop_right(),
                             push=lambda l, p: l.push(p), simulate=lambda l, n: l.simulate(n),
                             disabled=lambda l: l.nb_disabled)
-    assert (cycles, mig) == (o_cycles, o_mig)
+    # the number of migrations is a property of the trajectories; the number of cycles is not
+    # (which banked particles a layer picks first depends on the outbox order, unspecified here)
+    assert mig == o_mig
+    assert abs(cycles - o_cycles) <= max(4, o_cycles // 4)
     for g, o in zip(layers, o_layers):
-        q, k = g.weights_absorbed_q()
-        assert np.array_equal(q, o.tally_q)
+        assert np.array_equal(g.weights_absorbed_exact()[0], o.tally_exact)
         assert g.nb_disabled == o.nb_disabled
         assert g.counts()["events"] == o.stats()["events"]
         g.close()
@@ -206,7 +212,7 @@ def test_global_dx_decomposition_equals_single_layer(gpu):
     cfg = configs.reference_default(8000)
     with gpu_layer(cfg) as one:
         one.simulate(-1)
-        q1, _ = one.weights_absorbed_q()
+        q1, _ = one.weights_absorbed_exact()
         c1 = one.counts()
     for K in (2, 8):
         layers = [decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, K, r, cfg.nb_cells,
@@ -216,7 +222,7 @@ def test_global_dx_decomposition_equals_single_layer(gpu):
                   pop_left=lambda l: l.pop_left(), pop_right=lambda l: l.pop_right(),
                   push=lambda l, p: l.push(p), simulate=lambda l, n: l.simulate(n),
                   disabled=lambda l: l.nb_disabled)
-        qK = np.concatenate([l.weights_absorbed_q()[0] for l in layers])
+        qK = np.concatenate([l.weights_absorbed_exact()[0] for l in layers])
         assert np.array_equal(qK, q1)
         assert sum(l.counts()["events"] for l in layers) == c1["events"]
         assert sum(l.counts()["scatters"] for l in layers) == c1["scatters"]
@@ -239,8 +245,7 @@ def test_full_size_properties(gpu):
                 g.set_option("blocks_per_sm", 2)
             g.simulate(-1)
             c = g.counts()
-            q, k = g.weights_absorbed_q()
-            qs.append(q)
+            qs.append(g.weights_absorbed_exact()[0])
             assert c["n_left"] + c["n_right"] + c["n_dead"] == cfg.nb_particles
             assert c["nb_disabled"] == cfg.nb_particles and c["nb_active"] == 0
             total = float(np.sum(g.weights_absorbed_f64)) + c["w_left"] + c["w_right"] + c["w_dead"]

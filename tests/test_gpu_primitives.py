@@ -94,3 +94,29 @@ def test_device_birth_equals_reference_create_particles(gpu, mcb_lib, n):
     _abi.check(mcb_lib.mcb200_test_birth(gpu, cfg.x_ini, float(wmc), float(o.dx), n, 5127801,
                                          out.ctypes.data))
     assert out.tobytes() == want.tobytes()
+
+
+def test_exact_accumulator_device_equals_checker(gpu, mcb_lib):
+    """the long accumulator the tally uses: device sum of floats == the checker's 128-bit
+    integer sum, digit for digit, including negative deposits, carries and the dropped
+    sub-LSB bits."""
+    rng = np.random.default_rng(11)
+    for x in (
+        rng.random(1_000_000, dtype=np.float32) * np.float32(1e-5),
+        rng.integers(0x0d800000, 0x3f000000, size=1_000_000, dtype=np.uint32).view(np.float32),
+        np.concatenate([rng.random(100_000, dtype=np.float32), -rng.random(100_000, dtype=np.float32)]),
+        np.array([0.0, -0.0, 1e-30, 2.0 ** -97, 2.0 ** -110, 2.0 ** -125, 1e-45, 100.0, -100.0, 3e-39],
+                 dtype=np.float32),
+        np.full(300_000, 127.99 / 300_000 * 100, dtype=np.float32)[:3000],
+    ):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        want, want_d = pyoracle.accumulate_exact(x)
+        got = np.zeros(4, dtype=np.uint32)
+        d = C.c_double(0)
+        _abi.check(mcb_lib.mcb200_test_accumulate(gpu, x.ctypes.data, x.size, got.ctypes.data,
+                                                  C.byref(d)))
+        assert np.array_equal(got, want)
+        assert d.value == want_d
+    bad = np.array([1.0, 200.0], dtype=np.float32)
+    got = np.zeros(4, dtype=np.uint32)
+    assert mcb_lib.mcb200_test_accumulate(gpu, bad.ctypes.data, 2, got.ctypes.data, None) == _abi.ERR_RANGE

@@ -28,17 +28,14 @@ def apply_tables(layer, cfg, start=0):
         layer.absorption_rates[:] = cfg.absorption_rates[start:start + m]
 
 
-def make_oracle(cfg, world_size=1, world_rank=0, *, keep_border=True, log2_scale=None,
-                cls=OracleLayer):
-    from mc_mpi_b200.layer import split_cells, tally_log2_scale
+def make_oracle(cfg, world_size=1, world_rank=0, *, keep_border=True, cls=OracleLayer):
+    from mc_mpi_b200.layer import split_cells
     lay = cls.decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, world_size, world_rank,
                                cfg.nb_cells, cfg.nb_particles, cfg.particle_min_weight)
     start, _ = split_cells(cfg.nb_cells, world_size, world_rank)
     apply_tables(lay, cfg, start)
     if cls is OracleLayer:
         lay.set_keep_border(keep_border)
-        k = log2_scale if log2_scale is not None else tally_log2_scale(1.0 / cfg.nb_particles)
-        lay.set_tally_log2_scale(k)
     return lay
 
 

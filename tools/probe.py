@@ -12,11 +12,11 @@ n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
 name = sys.argv[2] if len(sys.argv) > 2 else "single_gpu_slab_1000"
 cfg = configs.BY_NAME[name]()
 cfg = cfg.with_particles(n)
-variants = [dict(tally_mode=1, warp_agg=0), dict(tally_mode=1, warp_agg=1),
-            dict(tally_mode=2, warp_agg=0), dict(tally_mode=2, warp_agg=1)]
+variants = [dict(tally_mode=1), dict(tally_mode=2)]
 shapes = [dict(block=256, blocks_per_sm=4), dict(block=128, blocks_per_sm=8),
           dict(block=512, blocks_per_sm=2), dict(block=1024, blocks_per_sm=1),
-          dict(block=256, blocks_per_sm=6), dict(block=256, blocks_per_sm=2)]
+          dict(block=256, blocks_per_sm=6), dict(block=256, blocks_per_sm=8),
+          dict(block=128, blocks_per_sm=12), dict(block=256, blocks_per_sm=2)]
 if len(sys.argv) > 3:
     shapes = shapes[:1]
 for v in variants:
