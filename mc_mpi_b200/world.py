@@ -1,0 +1,155 @@
+"""Multi-GPU driver: the slab domain-decomposed one contiguous sub-slab per rank / GPU.
+
+Stands in for the reference's worker loop (Worker::spin, src/worker_sync.cpp:24-135):
+simulate -> ship escapees to the neighbour ranks -> stop when the disabled counts of all
+ranks add up to nb_particles.  One process per GPU (torchrun); torch.distributed is the
+plumbing (NCCL over NVLink on GPUs, gloo on CPU for the host-logic tests).  The 1-D chain
+topology is the reference's: rank r only ever talks to r-1 and r+1.
+
+What is different from the MPI workers:
+  * escapees never touch the host: the tracking kernel compacts them into device outboxes,
+    `pop_*_device` packs the 24-byte wire records into the send buffer, NCCL moves them
+    GPU-to-GPU, `push_device` unpacks them into the neighbour's bank;
+  * every sub-slab tracks with the ONE global dx (decompose_domain(global_dx=True)), so a
+    K-GPU run reproduces the 1-GPU trajectories bit for bit (the reference's K-rank runs
+    differ from its 1-rank run by up to 5e-4 per cell, SURVEY hard part 3);
+  * the per-cycle bookkeeping (outbox sizes + disabled counts) is ONE small all-gather
+    instead of 4 Sendrecv + Barrier + Allreduce (src/worker_sync.cpp:47-120).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import configs as _configs
+from .layer import PARTICLE_DTYPE, Layer, decompose_domain, split_cells
+
+RECORD = PARTICLE_DTYPE.itemsize  # 24 bytes on the wire
+
+
+class SlabWorld:
+    def __init__(self, cfg: _configs.SlabConfig, *, rank=None, world_size=None, device=None,
+                 nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True):
+        self.cfg = cfg
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        self.per_cycle = int(nb_particles_per_cycle)
+        if layer is None:
+            layer = decompose_domain(
+                cfg.x_min, cfg.x_max, cfg.x_ini, self.world_size, self.rank, cfg.nb_cells,
+                cfg.nb_particles, cfg.particle_min_weight, device=device or 0,
+                global_dx=global_dx, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
+        self.layer = layer
+        # device-resident exchange when the layer lives on a GPU and the backend can move
+        # device memory; host staging otherwise (gloo tests)
+        self.on_device = isinstance(layer, Layer) and dist.get_backend(group) == "nccl"
+        self.tdev = torch.device("cuda", layer.device) if self.on_device else torch.device("cpu")
+        self._buf = {}
+        self.cycles = 0
+        self.migrations_out = 0
+        self.t_simulate = self.t_exchange = 0.0
+
+    # -- buffers ---------------------------------------------------------------------
+    def _buffer(self, name: str, n_records: int) -> torch.Tensor:
+        need = max(int(n_records), 1) * RECORD
+        b = self._buf.get(name)
+        if b is None or b.numel() < need:
+            b = torch.empty(int(need * 1.5) + RECORD, dtype=torch.uint8, device=self.tdev)
+            self._buf[name] = b
+        return b
+
+    # -- one cycle -------------------------------------------------------------------
+    def _exchange(self, counts: dict):
+        """ship particles_left / particles_right to rank-1 / rank+1, receive theirs
+        (src/worker_sync.cpp:47-108), return the global disabled count (:112-120)."""
+        K, r = self.world_size, self.rank
+        mine = torch.tensor([counts["n_outbox_left"], counts["n_outbox_right"],
+                             counts["nb_disabled"]], dtype=torch.int64, device=self.tdev)
+        table = torch.empty(K * 3, dtype=torch.int64, device=self.tdev)
+        dist.all_gather_into_tensor(table, mine, group=self.group)
+        table = table.view(K, 3).cpu()
+        n_send = {-1: int(table[r, 0]), +1: int(table[r, 1])}
+        n_recv = {-1: int(table[r - 1, 1]) if r > 0 else 0,
+                  +1: int(table[r + 1, 0]) if r + 1 < K else 0}
+        ops, recv_bufs = [], {}
+        for side, d in ((0, -1), (1, +1)):
+            peer = r + d
+            if 0 <= peer < K:
+                if n_send[d] > 0:
+                    sb = self._buffer(f"send{d}", n_send[d])
+                    if self.on_device:
+                        got = self.layer.pop_device(side, sb.data_ptr(), n_send[d])
+                    else:
+                        arr = self.layer.pop_left() if side == 0 else self.layer.pop_right()
+                        got = len(arr)
+                        sb[: got * RECORD] = torch.from_numpy(
+                            np.frombuffer(arr.tobytes(), dtype=np.uint8).copy())
+                    assert got == n_send[d]
+                    ops.append(dist.P2POp(dist.isend, sb[: got * RECORD], self._global(peer),
+                                          group=self.group))
+                    self.migrations_out += got
+                if n_recv[d] > 0:
+                    rb = self._buffer(f"recv{d}", n_recv[d])
+                    recv_bufs[d] = rb
+                    ops.append(dist.P2POp(dist.irecv, rb[: n_recv[d] * RECORD],
+                                          self._global(peer), group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            if self.on_device:
+                torch.cuda.current_stream(self.tdev).synchronize()
+        for d, rb in recv_bufs.items():
+            if self.on_device:
+                self.layer.push_device(rb.data_ptr(), n_recv[d])
+            else:
+                raw = rb[: n_recv[d] * RECORD].numpy().tobytes()
+                self.layer.push(np.frombuffer(raw, dtype=PARTICLE_DTYPE))
+        return int(table[:, 2].sum())
+
+    def _global(self, group_rank: int) -> int:
+        return dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+
+    def spin(self, max_cycles=10_000_000) -> dict:
+        """Worker::spin: cycle until every source particle is disabled somewhere."""
+        total = self.cfg.nb_particles
+        while self.cycles < max_cycles:
+            t0 = time.perf_counter()
+            c = self.layer.simulate(self.per_cycle)
+            t1 = time.perf_counter()
+            disabled = self._exchange(c)
+            t2 = time.perf_counter()
+            self.t_simulate += t1 - t0
+            self.t_exchange += t2 - t1
+            self.cycles += 1
+            if disabled == total:
+                break
+        else:
+            raise RuntimeError("SlabWorld.spin: did not terminate")
+        return self.summary()
+
+    # -- results ---------------------------------------------------------------------
+    def summary(self) -> dict:
+        c = self.layer.counts()
+        return {"rank": self.rank, "cycles": self.cycles, "migrations_out": self.migrations_out,
+                "t_simulate": self.t_simulate, "t_exchange": self.t_exchange, **c}
+
+    def gather_weights_absorbed(self):
+        """Worker::gather_weights_absorbed (src/worker.cpp:183-216): the disjoint per-rank
+        slices concatenated on rank 0 (None elsewhere); float64 view of the exact tally."""
+        K = self.world_size
+        mine = torch.from_numpy(np.ascontiguousarray(self.layer.weights_absorbed_f64))
+        sizes = [split_cells(self.cfg.nb_cells, K, r)[1] for r in range(K)]
+        m_max = max(sizes)
+        pad = torch.zeros(m_max, dtype=torch.float64)
+        pad[: mine.numel()] = mine
+        pad = pad.to(self.tdev)
+        out = torch.empty(K * m_max, dtype=torch.float64, device=self.tdev)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        if self.rank != 0:
+            return None
+        out = out.cpu().view(K, m_max).numpy()
+        return np.concatenate([out[r, : sizes[r]] for r in range(K)])
