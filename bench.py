@@ -169,7 +169,7 @@ def run_gpu_arm(args):
     import torch
 
     from mc_mpi_b200 import _abi
-    from mc_mpi_b200.layer import PARTICLE_DTYPE, decompose_domain
+    from mc_mpi_b200.layer import PARTICLE_DTYPE, Layer, decompose_domain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,9 +276,8 @@ def run_gpu_arm(args):
         dx = float(layer.dx)
         _abi.check(_abi.lib().mcb200_test_birth(local_rank, cfg.x_ini, float(np.float32(1.0 / n_e2e)),
                                                 dx, n_e2e, 5127801, host.data_ptr()))
-        e_layer = decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, 1, 0, cfg.nb_cells, 0,
-                                   cfg.particle_min_weight, device=local_rank, sigs=cfg.sigs,
-                                   absorption_rates=cfg.absorption_rates)
+        e_layer = Layer(cfg.x_min, cfg.x_max, 0, cfg.nb_cells, cfg.particle_min_weight,
+                        device=local_rank, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
         wa = np.empty(cfg.nb_cells, dtype=np.float32)
 
         def e2e_step():
