@@ -102,6 +102,14 @@ int mcb200_layer_set_cross_sections(mcb200_layer *l, const float *sigs,
 int mcb200_layer_get_cross_sections(mcb200_layer *l, float *sigs_out,
                                     float *absorption_rates_out);
 
+/* the cross-sections Layer::Layer hard-codes (src/layer.cpp:53-63) for a layer of
+ * m cells spanning [x_min, x_max]: sigs[i] = expf(-x_mid_i), absorption = 0.5.
+ * Host-only helper (no GPU needed).  A K-GPU run that must equal the 1-GPU run
+ * slices the table of the WHOLE slab instead of letting every sub-slab recompute
+ * its own from rounded bounds (which moves ~20-30 % of the entries by 1 ulp). */
+int mcb200_default_cross_sections(float x_min, float x_max, int32_t m,
+                                  float *sigs_out, float *absorption_rates_out);
+
 /* ---- particle sources ------------------------------------------------- */
 /* Layer::create_particles(x_ini, wmc, n, seed), src/layer.cpp:71-82: registers
  * n unborn particles; they are born ON THE DEVICE (rnd_seed chain via LCG

@@ -63,6 +63,7 @@ SYMBOLS = {
     "mcb200_layer_clone": (C.c_int, [_P, C.POINTER(_P)]),
     "mcb200_layer_set_cross_sections": (C.c_int, [_P, _P, _P]),
     "mcb200_layer_get_cross_sections": (C.c_int, [_P, _P, _P]),
+    "mcb200_default_cross_sections": (C.c_int, [_F, _F, _I32, _P, _P]),
     "mcb200_layer_create_particles": (C.c_int, [_P, _F, _F, _I64, C.c_uint64]),
     "mcb200_layer_push": (C.c_int, [_P, _P, _I64]),
     "mcb200_layer_push_device": (C.c_int, [_P, _P, _I64]),

@@ -227,7 +227,17 @@ static Layer decompose_impl(real_t x_min, real_t x_max, real_t x_ini, int world_
 
   Layer layer(x_min + start_index * dx, x_min + (start_index + nb_my_cells) * dx, start_index,
               nb_my_cells, particle_min_weight);
-  if (global_dx) layer.set_edge_dx(dx);
+  if (global_dx) {
+    // one dx and one cross-section table for the whole slab, sliced per layer, so that K
+    // layers reproduce the single-layer trajectories and tallies bit for bit
+    layer.set_edge_dx(dx);
+    std::vector<real_t> s((size_t)nb_cells), a((size_t)nb_cells);
+    die_on(mcb200_default_cross_sections(x_min, x_max, nb_cells, s.data(), a.data()),
+           "default_cross_sections");
+    layer.sigs.assign(s.begin() + start_index, s.begin() + start_index + nb_my_cells);
+    layer.absorption_rates.assign(a.begin() + start_index,
+                                  a.begin() + start_index + nb_my_cells);
+  }
   if ((cell_ini >= start_index) && (cell_ini < start_index + nb_my_cells)) {
     seed_t seed = 5127801;  // :36
     layer.create_particles(x_ini, 1.0 / nb_particles, nb_particles, seed);

@@ -1,6 +1,6 @@
 // mcb_kernels.cu -- hand-written sm_100a kernels of the particle-tracking path.
 //
-// track_kernel<SHARED> is the product: a persistent, history-based
+// track_kernel<SHARED, MAXB> is the product: a persistent, history-based
 // tracking kernel.  Each lane owns one particle in registers and runs the
 // reference's event loop (src/layer.cpp:123-218) until the particle leaves the
 // sub-slab or drops below particle_min_weight; finished lanes are retired and
@@ -30,7 +30,8 @@ namespace mcb {
 // significand sits inside one digit, two when it straddles; carries ripple by
 // further adds only when a digit wraps.  The final digits do not depend on the
 // interleaving: every step is an exact add modulo 2^128.
-__device__ __forceinline__ void acc_add(unsigned *w, int stride, float v, unsigned *range_flag) {
+// general case: zeros, deposits below 2^-97, negative deposits, out-of-range values
+__device__ __noinline__ void acc_add_slow(unsigned *w, int stride, float v, unsigned *range_flag) {
   const unsigned b = __float_as_uint(v);
   const unsigned e = (b >> 23) & 0xffu;
   unsigned mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
@@ -65,6 +66,36 @@ __device__ __forceinline__ void acc_add(unsigned *w, int stride, float v, unsign
   }
 }
 
+// a carry out of digit j-1 rippling upwards (a digit wraps once in 2^32 units: rare)
+__device__ __noinline__ void acc_ripple(unsigned *w, int stride, int j) {
+  for (; j < kAccDigits; ++j)
+    if (atomicAdd(&w[j * stride], 1u) != 0xffffffffu) break;
+}
+
+// The hot deposit: v positive, normal, in [2^-97, 2^7) -- every per-event dw of a real
+// run.  The biased exponent with the sign bit on top is range-checked with ONE unsigned
+// compare; then 1 ATOMS.ADD when the significand sits inside a digit, 2 when it straddles.
+__device__ __forceinline__ void acc_add(unsigned *w, int stride, float v, unsigned *range_flag) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned pos = (b >> 23) - (unsigned)(150 + kAccLsbLog2);  // exponent (and sign) - 30
+  if (pos <= (unsigned)(32 * kAccDigits - 25)) {
+    const unsigned mant = (b & 0x7fffffu) | 0x800000u;
+    const int j = (int)(pos >> 5);
+    const unsigned o = pos & 31u;
+    const unsigned lo = mant << o;
+    const unsigned hi = __funnelshift_l(mant, 0u, o);  // bits pushed into the next digit
+    unsigned *d = &w[j * stride];
+    const unsigned old = atomicAdd(d, lo);
+    const unsigned c = hi + (old > ~lo ? 1u : 0u);
+    if (c != 0u && j < kAccDigits - 1) {
+      const unsigned old2 = atomicAdd(d + stride, c);
+      if (old2 > ~c) acc_ripple(w, stride, j + 2);
+    }
+  } else {
+    acc_add_slow(w, stride, v, range_flag);
+  }
+}
+
 // add a whole accumulator (digits d[0..3] of one cell) into another one
 __device__ __forceinline__ void acc_merge(unsigned *w, int stride, const unsigned d[kAccDigits]) {
   unsigned c = 0u;
@@ -92,8 +123,12 @@ struct TrackSmem {
 
 // ----------------------------------------------------------- the hot path --
 
-template <bool SHARED>
-__global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
+// MAXB = largest CTA this instantiation is launched with.  The 256-thread one is the
+// workhorse: 6 CTAs per SM (1536 resident threads) caps it at 40 registers, which is what
+// the event loop needs; the 1024-thread one exists for sub-slabs whose CTA-private tally
+// only fits once per SM.
+template <bool SHARED, int MAXB>
+__global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const TrackParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem *sm = reinterpret_cast<TrackSmem *>(smem_raw);
   CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(TrackSmem));
@@ -127,7 +162,10 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
 
   for (;;) {
     // ---- liveness: loop condition of simulate_particle, src/layer.cpp:195-197
-    const bool alive = active && (wmc >= minw) && (idx >= lo) && (idx < hi);
+    const bool alive = active && (wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)p.m);
+    // steady state: all 32 lanes carry a live history -> one vote, straight to the event.
+    // Retire / refill / exit only run on the iterations where some lane is not alive.
+    if (!__all_sync(MCB_FULL, alive)) {
     const bool fin = active && !alive;
     const unsigned fm = __ballot_sync(MCB_FULL, fin);
     if (fm) {
@@ -187,6 +225,7 @@ __global__ void __launch_bounds__(1024, 1) track_kernel(const TrackParams p) {
       continue;  // fresh lanes go through the liveness test first
     }
     if (im == MCB_FULL) break;  // bank handed out and every lane retired
+    }
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
@@ -260,8 +299,9 @@ size_t track_smem_bytes(int tally_mode, int m) {
 }
 
 typedef void (*TrackFn)(const TrackParams);
-static TrackFn track_fn(int mode) {
-  return mode == kTallyShared ? track_kernel<true> : track_kernel<false>;
+static TrackFn track_fn(int mode, int block) {
+  if (block <= 256) return mode == kTallyShared ? track_kernel<true, 256> : track_kernel<false, 256>;
+  return mode == kTallyShared ? track_kernel<true, 1024> : track_kernel<false, 1024>;
 }
 
 cudaError_t track_configure(int device, int m, int want_mode, int want_block,
@@ -298,7 +338,7 @@ cudaError_t track_configure(int device, int m, int want_mode, int want_block,
   out->block = block;
   out->grid = prop.multiProcessorCount * bps;
   out->smem = smem;
-  return cudaFuncSetAttribute(track_fn(mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(track_fn(mode, block), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem);
 }
 
@@ -306,7 +346,7 @@ cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStrea
   if (p.take_count <= 0) return cudaSuccess;
   long long need = (p.take_count + cfg.block - 1) / cfg.block;
   int grid = (int)(need < (long long)cfg.grid ? need : (long long)cfg.grid);
-  track_fn(cfg.tally_mode)<<<grid, cfg.block, cfg.smem, stream>>>(p);
+  track_fn(cfg.tally_mode, cfg.block)<<<grid, cfg.block, cfg.smem, stream>>>(p);
   return cudaGetLastError();
 }
 

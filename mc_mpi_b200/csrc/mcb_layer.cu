@@ -370,6 +370,19 @@ int mcb200_device_count(void) {
   return n;
 }
 
+int mcb200_default_cross_sections(float x_min, float x_max, int32_t m, float *sigs_out,
+                                  float *absorption_rates_out) {
+  if (m <= 0) return fail(MCB200_ERR_INVALID, "default_cross_sections: m must be positive");
+  const float ctor_dx = (x_max - x_min) / m;  // Layer::dx, src/layer.cpp:47
+  for (int i = 0; i < m; ++i) {
+    const float base = x_min + (i * ctor_dx);
+    const float x_mid = (float)((double)base + 0.5 * (double)ctor_dx);  // :58
+    if (sigs_out) sigs_out[i] = expf(-x_mid);                            // :59
+    if (absorption_rates_out) absorption_rates_out[i] = 0.5f;            // :63
+  }
+  return MCB200_OK;
+}
+
 int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   if (!d || !out) return fail(MCB200_ERR_INVALID, "create: null argument");
   *out = nullptr;
@@ -399,12 +412,11 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   l->sigs.resize((size_t)l->m);
   l->absorption_rates.resize((size_t)l->m);
   // cross-sections default to the reference's hard-coded ones (src/layer.cpp:53-63)
-  for (int i = 0; i < l->m; ++i) {
-    const float base = d->x_min + (i * ctor_dx);
-    const float x_mid = (float)((double)base + 0.5 * (double)ctor_dx);  // :58
-    l->sigs[(size_t)i] = d->sigs ? d->sigs[i] : expf(-x_mid);            // :59
-    l->absorption_rates[(size_t)i] = d->absorption_rates ? d->absorption_rates[i] : 0.5f;
-  }
+  mcb200_default_cross_sections(d->x_min, d->x_max, d->m, l->sigs.data(),
+                                l->absorption_rates.data());
+  if (d->sigs) l->sigs.assign(d->sigs, d->sigs + l->m);
+  if (d->absorption_rates)
+    l->absorption_rates.assign(d->absorption_rates, d->absorption_rates + l->m);
   l->seed_jump = mcb::make_jump_table(mcb::kSeedG, mcb::kSeedC);
 
   DeviceGuard g(l->device);

@@ -69,6 +69,18 @@ static __constant__ MathTables c_math_tables = {
      0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
      0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull}};
 
+// polynomial / reduction constants of the two routines, in the constant bank so that the
+// FP64 instructions take them as c[bank][offset] operands instead of re-materialising
+// 64-bit immediates in registers on every event
+struct MathConsts {
+  double ln2, a0, a1, a2;                 // e_logf_data.c: ln2, poly[0..2]
+  double inv_ln2_n, shift, c0, c1, c2;    // e_exp2f_data.c: invln2_scaled, shift, poly_scaled
+};
+static __constant__ MathConsts c_mc = {
+    0x1.62e42fefa39efp-1, -0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2,
+    0x1.71547652b82fep+0 * 32, 0x1.8p+52, 0x1.c6af84b912394p-5 / 32 / 32 / 32,
+    0x1.ebfce50fac4f3p-3 / 32 / 32, 0x1.62e42ff0c52d6p-1 / 32};
+
 // copy the 512-byte tables into shared memory (lane-divergent indices would
 // serialise on the constant cache)
 __device__ __forceinline__ void load_math_tables(MathTables *s) {
@@ -134,9 +146,7 @@ __host__ __device__ inline uint64_t jump_state(const JumpTable &t, uint64_t k, u
 // glibc sysdeps/ieee754/flt-32/e_logf.c (LOGF_TABLE_BITS 4, POLY_ORDER 4).
 // Domain on the path: h = rnd_real() in {+0} U [2^-63, 1] (src/layer.cpp:136).
 __device__ __forceinline__ float logf_glibc(float x, const MathTables *tb) {
-  const double ln2 = 0x1.62e42fefa39efp-1;
-  const double a0 = -0x1.00ea348b88334p-2, a1 = 0x1.5575b0be00b6ap-2,
-               a2 = -0x1.ffffef20a4123p-2;
+  const double ln2 = c_mc.ln2, a0 = c_mc.a0, a1 = c_mc.a1, a2 = c_mc.a2;
   const uint32_t ix = __float_as_uint(x);
   const uint32_t tmp = ix - 0x3f330000u;
   const uint32_t i = (tmp >> 19) & 15u;
@@ -163,11 +173,8 @@ __device__ __forceinline__ float logf_glibc(float x, const MathTables *tb) {
 // path: -sig_a*di in [-inf, +0] (src/layer.cpp:175); the result only enters
 // as 1 - expf().
 __device__ __forceinline__ float expf_glibc_nonpos(float x, const MathTables *tb) {
-  const double shift = 0x1.8p+52;
-  const double inv_ln2_n = 0x1.71547652b82fep+0 * 32;
-  const double c0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32;
-  const double c1 = 0x1.ebfce50fac4f3p-3 / 32 / 32;
-  const double c2 = 0x1.62e42ff0c52d6p-1 / 32;
+  const double shift = c_mc.shift, inv_ln2_n = c_mc.inv_ln2_n;
+  const double c0 = c_mc.c0, c1 = c_mc.c1, c2 = c_mc.c2;
   const uint32_t ix = __float_as_uint(x);
   // (double)x by re-biasing; +-0 and subnormals map to ~2^-896 instead, which
   // gives the same 1.0f (expf of anything below 2^-126 in magnitude is 1.0f)

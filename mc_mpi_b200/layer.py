@@ -184,6 +184,16 @@ class Layer:
         return int(_abi.lib().mcb200_layer_stream(self._h) or 0)
 
 
+def default_cross_sections(x_min, x_max, m):
+    """(sigs, absorption_rates) Layer::Layer hard-codes for m cells on [x_min, x_max]
+    (src/layer.cpp:53-63), computed by the library with the libm the reference links."""
+    s = np.empty(int(m), dtype=np.float32)
+    a = np.empty(int(m), dtype=np.float32)
+    check(_abi.lib().mcb200_default_cross_sections(float(f32(x_min)), float(f32(x_max)), int(m),
+                                                   s.ctypes.data, a.ctypes.data))
+    return s, a
+
+
 def split_cells(nb_cells: int, world_size: int, world_rank: int):
     """cells of one rank, src/layer.cpp:24-27 -> (start_index, nb_my_cells)."""
     cells_per_layer = nb_cells // world_size
@@ -211,6 +221,12 @@ def decompose_domain(x_min, x_max, x_ini, world_size, world_rank, nb_cells, nb_p
     hi = f32(x_min + f32(start_index + nb_my_cells) * dx)
     wmc = f32(1.0 / nb_particles)                                # :38, double -> float
     sl = slice(start_index, start_index + nb_my_cells)
+    if global_dx and (sigs is None or absorption_rates is None):
+        # the table of the WHOLE slab, sliced: per-sub-slab recomputation (the reference's
+        # K-rank behaviour) moves a quarter of the entries by 1 ulp
+        s_all, a_all = default_cross_sections(x_min, x_max, nb_cells)
+        sigs = s_all if sigs is None else sigs
+        absorption_rates = a_all if absorption_rates is None else absorption_rates
     layer = Layer(lo, hi, start_index, nb_my_cells, particle_min_weight,
                   device=device, dx=dx if global_dx else None, keep_border=keep_border,
                   sigs=None if sigs is None else np.asarray(sigs, dtype=np.float32)[sl],

@@ -36,9 +36,18 @@ def main():
                                cfg.particle_min_weight, device=local, sigs=cfg.sigs,
                                absorption_rates=cfg.absorption_rates)
         c = one.simulate(-1)
-        ok = np.array_equal(one.weights_absorbed_f64, wa)
+        w1 = one.weights_absorbed_f64
+        ok = np.array_equal(w1, wa)
         ev, sc, mig, nl, nr, nd = stats.tolist()
-        ok &= (ev, sc, nl, nr, nd) == (c["events"], c["scatters"], c["n_left"], c["n_right"], c["n_dead"])
+        same_counts = (ev, sc, nl, nr, nd) == (c["events"], c["scatters"], c["n_left"], c["n_right"], c["n_dead"])
+        if not ok or not same_counts:
+            bad = np.nonzero(w1 != wa)[0]
+            print("[multi-gpu parity] counts K-GPU", (ev, sc, nl, nr, nd), "1-GPU",
+                  (c["events"], c["scatters"], c["n_left"], c["n_right"], c["n_dead"]))
+            print("[multi-gpu parity] differing cells:", len(bad), bad[:10],
+                  "max rel", float(np.max(np.abs(w1 - wa) / w1)) if len(bad) else 0.0,
+                  "sum K", float(wa.sum()), "sum 1", float(w1.sum()))
+        ok &= same_counts
         print(f"[multi-gpu parity] K={K} config={cfg.name} histories={n} cycles={s['cycles']} "
               f"migrations/history={mig / n:.3f} events={ev} tally_bit_exact={ok}", flush=True)
         one.close()
