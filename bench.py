@@ -267,6 +267,15 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         achieved_min = float(t.item())
     value = n_hist * args.steps / (dev_ms * 1e-3)
+    world_info = None
+    if world > 1:
+        world_info = {"cycles": sw.cycles,
+                      "t_simulate_s_max": max_over_ranks(sw.t_simulate),
+                      "t_exchange_s_max": max_over_ranks(sw.t_exchange),
+                      "track_ms_max": max_over_ranks(track_ms),
+                      "track_ms_sum": sum_over_ranks(track_ms),
+                      "note": "host wall-clock split of SlabWorld.spin over warm-up + timed steps; "
+                              "track_ms = tracking-kernel time of the timed steps"}
 
     # ---- end-to-end arm: host buffers through the reference-facing interface ------------
     e2e = None
@@ -346,6 +355,7 @@ def run_gpu_arm(args):
                                   f"({launches} launches, {track_ms / max(launches, 1):.3f} ms avg"
                                   f"{', min over ranks' if world > 1 else ''})"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "world": world_info,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

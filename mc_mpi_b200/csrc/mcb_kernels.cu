@@ -12,8 +12,9 @@
 //    * one EXACT deposit into the CTA-private per-cell tally in shared memory
 //      (128-bit long accumulator in 32-bit digits: 1-2 native ATOMS.ADD plus
 //      rare carries), merged into the global tally ONCE per CTA,
-//    * escapees compacted with ballot/popc prefix sums into contiguous
-//      left / right outboxes (one global atomic per warp per retire event).
+//    * escapees compacted with ballot/popc prefix sums into per-CTA outbox stripes
+//      (one SHARED-memory atomic per warp per retire event, no global atomic), packed
+//      into contiguous left / right send buffers by gather_stripes_kernel.
 // Nothing on this path is a contraction: no tensor cores by design.
 #include "mcb_kernels.cuh"
 
@@ -119,6 +120,8 @@ struct TrackSmem {
   MathTables math;
   unsigned int n_cls[3];
   unsigned int pad;
+  unsigned int out_n[2];   // fill of this CTA's outbox stripes
+  unsigned int pad2[2];
 };
 
 // ----------------------------------------------------------- the hot path --
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
 
   load_math_tables(&sm->math);
   if (threadIdx.x < 3) sm->n_cls[threadIdx.x] = 0u;
+  if (threadIdx.x < 2) sm->out_n[threadIdx.x] = 0u;
   if (SHARED) {
     for (int c = threadIdx.x; c < p.m; c += blockDim.x) s_xs[c] = p.xs[c];
     for (int c = threadIdx.x; c < kAccDigits * ncell; c += blockDim.x) acc[c] = 0u;
@@ -158,6 +162,8 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
   int idx = 0;
   bool active = false;
   bool exhausted = false;  // warp-uniform: the bank range has been handed out
+  bool drained = false;    // warp-uniform: the global cursor has passed the end of the range
+  unsigned long long w_next = 0ull, w_end = 0ull;  // this warp's chunk of bank slots
   unsigned n_ev = 0, n_sc = 0;
 
   for (;;) {
@@ -182,18 +188,28 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
         const int leader = __ffs(cm) - 1;
         if (lane == leader) atomicAdd(&sm->n_cls[c], (unsigned)cnt);
         if (c < 2 && p.write_side[c]) {
-          // warp-aggregated append: one reservation per warp, ranks by popc
-          unsigned long long base = 0ull;
-          if (lane == leader)
-            base = atomicAdd(&p.ctr->out_n[c], (unsigned long long)cnt);
+          // warp-aggregated append to this CTA's stripe: ONE shared-memory atomic per warp,
+          // ranks by popc; the records are the 24-byte wire format
+          unsigned base = 0u;
+          if (lane == leader) base = atomicAdd(&sm->out_n[c], (unsigned)cnt);
           base = __shfl_sync(MCB_FULL, base, leader);
           if (mine) {
-            const long long pos = (long long)base + __popc(cm & lt_mask);
-            if (pos < p.out_cap[c]) {
-              p.out_seed[c][pos] = seed;
-              p.out_st[c][pos] = make_float4(x, mu, wmc, __int_as_float(idx));
-            } else {
-              atomicExch(&p.ctr->overflow, 1u);
+            const unsigned my = base + (unsigned)__popc(cm & lt_mask);
+            long long slot = -1;
+            if (my < (unsigned)p.stripe_cap) {
+              slot = (long long)blockIdx.x * p.stripe_cap + my;
+            } else {  // stripe full (unbalanced CTAs): the common overflow segment
+              const unsigned o = atomicAdd(&p.stripe_n[c * (kStripes + 1) + kStripes], 1u);
+              if ((long long)o < p.ovf_cap) slot = p.ovf_base + o;
+              else atomicExch(&p.ctr->overflow, 1u);
+            }
+            if (slot >= 0) {
+              unsigned long long *rec = p.out_rec[c] + 3 * slot;
+              rec[0] = seed;
+              rec[1] = (unsigned long long)__float_as_uint(x) |
+                       ((unsigned long long)__float_as_uint(mu) << 32);
+              rec[2] = (unsigned long long)__float_as_uint(wmc) |
+                       ((unsigned long long)(unsigned)idx << 32);
             }
           }
         }
@@ -204,15 +220,21 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
     // ---- refill idle lanes from the bank (coalesced 8 B + 16 B per lane)
     const unsigned im = __ballot_sync(MCB_FULL, !active);
     if (im && !exhausted) {
-      const int cnt = __popc(im);
-      unsigned long long base = 0ull;
-      if (lane == 0) base = atomicAdd(&p.ctr->cursor, (unsigned long long)cnt);
-      base = __shfl_sync(MCB_FULL, base, 0);
-      if (base + (unsigned long long)cnt >= take) exhausted = true;
+      // bank slots come in warp-private chunks: one global atomic per kWorkChunk particles
+      if (w_next == w_end && !drained) {
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd(&p.ctr->cursor, (unsigned long long)kWorkChunk);
+        base = __shfl_sync(MCB_FULL, base, 0);
+        w_next = base < take ? base : take;
+        w_end = base + kWorkChunk < take ? base + kWorkChunk : take;
+        drained = base + kWorkChunk >= take;
+      }
+      const unsigned long long avail = w_end - w_next;
+      const unsigned long long cnt = (unsigned long long)__popc(im);
       if (!active) {
-        const unsigned long long id = base + (unsigned long long)__popc(im & lt_mask);
-        if (id < take) {
-          const long long slot = p.take_base + (long long)id;
+        const unsigned long long r = (unsigned long long)__popc(im & lt_mask);
+        if (r < avail) {
+          const long long slot = p.take_base + (long long)(w_next + r);
           seed = __ldcs(&p.bank_seed[slot]);
           const float4 st = __ldcs(&p.bank_st[slot]);
           x = st.x;
@@ -222,6 +244,8 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
           active = true;
         }
       }
+      w_next += cnt < avail ? cnt : avail;
+      if (w_next == w_end && drained) exhausted = true;
       continue;  // fresh lanes go through the liveness test first
     }
     if (im == MCB_FULL) break;  // bank handed out and every lane retired
@@ -289,6 +313,11 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
     const int c = threadIdx.x;
     if (sm->n_cls[c]) atomicAdd(&p.ctr->n_cls[c], (unsigned long long)sm->n_cls[c]);
   }
+  if (threadIdx.x < 2) {
+    const unsigned n = sm->out_n[threadIdx.x];
+    p.stripe_n[threadIdx.x * (kStripes + 1) + blockIdx.x] =
+        n < (unsigned)p.stripe_cap ? n : (unsigned)p.stripe_cap;
+  }
 }
 
 size_t track_smem_bytes(int tally_mode, int m) {
@@ -337,16 +366,58 @@ cudaError_t track_configure(int device, int m, int want_mode, int want_block,
   out->tally_mode = mode;
   out->block = block;
   out->grid = prop.multiProcessorCount * bps;
+  if (out->grid > kStripes) out->grid = kStripes;
   out->smem = smem;
   return cudaFuncSetAttribute(track_fn(mode, block), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem);
 }
 
+int track_grid(const TrackLaunch &cfg, long long take) {
+  long long need = (take + cfg.block - 1) / cfg.block;
+  if (need < 1) need = 1;
+  return (int)(need < (long long)cfg.grid ? need : (long long)cfg.grid);
+}
+
 cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStream_t stream) {
   if (p.take_count <= 0) return cudaSuccess;
-  long long need = (p.take_count + cfg.block - 1) / cfg.block;
-  int grid = (int)(need < (long long)cfg.grid ? need : (long long)cfg.grid);
-  track_fn(cfg.tally_mode, cfg.block)<<<grid, cfg.block, cfg.smem, stream>>>(p);
+  track_fn(cfg.tally_mode, cfg.block)<<<track_grid(cfg, p.take_count), cfg.block, cfg.smem,
+                                        stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- gather --
+
+// CTA s packs segment s (stripe s, or the overflow segment for s == nstripes) behind the
+// segments before it: an exclusive prefix over <= kStripes + 1 fills (block reduction),
+// then a linear, coalesced copy of 8-byte words.
+__global__ void __launch_bounds__(256) gather_stripes_kernel(
+    const unsigned long long *__restrict__ scratch, const unsigned *__restrict__ stripe_n,
+    int nstripes, int stripe_cap, long long ovf_base, unsigned long long *__restrict__ settled,
+    long long settled_n, unsigned long long *out_total) {
+  __shared__ unsigned long long s_part[8];
+  const int seg = blockIdx.x;
+  unsigned long long before = 0ull;
+  for (int t = threadIdx.x; t < seg; t += blockDim.x) before += stripe_n[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(MCB_FULL, before, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = before;
+  __syncthreads();
+  before = 0ull;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) before += s_part[w];
+  const unsigned n = stripe_n[seg == nstripes ? kStripes : seg];
+  const long long src = seg == nstripes ? ovf_base : (long long)seg * stripe_cap;
+  const unsigned long long *from = scratch + 3 * src;
+  unsigned long long *to = settled + 3 * (settled_n + (long long)before);
+  for (unsigned i = threadIdx.x; i < 3u * n; i += blockDim.x) to[i] = from[i];
+  if (seg == nstripes && threadIdx.x == 0) *out_total = before + n;
+}
+
+cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsigned *stripe_n,
+                                  int nstripes, int stripe_cap, long long ovf_base,
+                                  unsigned long long *settled, long long settled_n,
+                                  unsigned long long *out_total, cudaStream_t stream) {
+  gather_stripes_kernel<<<nstripes + 1, 256, 0, stream>>>(scratch, stripe_n, nstripes, stripe_cap,
+                                                          ovf_base, settled, settled_n, out_total);
   return cudaGetLastError();
 }
 

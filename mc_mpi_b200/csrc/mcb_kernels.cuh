@@ -25,10 +25,19 @@ constexpr int kAccLsbLog2 = -120;
 // histories classified left / right / dead
 constexpr int kAccExtra = 3;
 
+// Escapees leave the tracking kernel through per-CTA "stripes": CTA b appends to its own
+// region [b*stripe_cap, (b+1)*stripe_cap) of the launch's scratch outbox with a SHARED-memory
+// counter (no global atomic on the path; a stripe that fills up spills into one common
+// overflow segment).  gather_stripes then packs the stripes into the layer's contiguous
+// outbox of 24-byte wire records.  kStripes bounds the grid of the tracking kernel.
+constexpr int kStripes = 2048;
+// bank slots are handed to warps in chunks of kWorkChunk (one global atomic per chunk)
+constexpr int kWorkChunk = 64;
+
 // Device counters of one layer; zeroed per tracking launch, read back after.
 struct DevCounters {
   unsigned long long cursor;      // next unclaimed slot of the launch's bank range
-  unsigned long long out_n[2];    // fill of the left / right outbox (persist across launches)
+  unsigned long long out_total[2];  // escapees of this launch per side (written by gather_stripes)
   unsigned long long n_cls[3];    // histories classified left / right / dead
   unsigned long long events;
   unsigned long long scatters;
@@ -57,9 +66,11 @@ struct TrackParams {
   float minw;            // particle_min_weight
   // outputs
   unsigned *acc;         // [kAccDigits][m + kAccExtra] digits, digit-major
-  unsigned long long *out_seed[2];
-  float4 *out_st[2];
-  long long out_cap[2];
+  unsigned long long *out_rec[2];  // scratch outbox per side, 24-byte records (3 words each)
+  unsigned *stripe_n;    // [2][kStripes + 1] fills; entry kStripes = the overflow segment
+  int stripe_cap;        // records per stripe
+  long long ovf_base;    // first record of the overflow segment (= grid * stripe_cap)
+  long long ovf_cap;     // its capacity
   int write_side[2];     // 0: global border, escapees are only counted
   DevCounters *ctr;
 };
@@ -76,8 +87,16 @@ struct TrackLaunch {
 size_t track_smem_bytes(int tally_mode, int m);
 cudaError_t track_configure(int device, int m, int want_mode, int want_block,
                             int want_blocks_per_sm, TrackLaunch *out);
+// grid actually used for `take` particles (<= cfg.grid <= kStripes)
+int track_grid(const TrackLaunch &cfg, long long take);
 cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg,
                          cudaStream_t stream);
+// pack the stripes (+ overflow segment) of one side behind `settled_n` records of the
+// layer's contiguous outbox; adds the number of records to *out_total
+cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsigned *stripe_n,
+                                  int nstripes, int stripe_cap, long long ovf_base,
+                                  unsigned long long *settled, long long settled_n,
+                                  unsigned long long *out_total, cudaStream_t stream);
 
 // device-side birth (src/layer.cpp:101-120): particle i of the batch gets
 // seed = rnd_seed^(i+1)(chain_state), mu from the first rnd_real draw

@@ -4,7 +4,8 @@
 // and the tally resident in HBM:
 //
 //   bank      seed[cap] (u64) + st[cap] (float4 {x, mu, wmc, bits(index)})
-//   outboxes  same layout, one per side, filled by the tracking kernel
+//   outboxes  contiguous 24-byte wire records per side (packed from the tracking kernel's
+//             per-CTA stripes by gather_stripes after every launch)
 //   tally     u32[4][m+3] exact long accumulator (mcb_kernels.cuh)
 //   xs        float2[m] {sig_a, sig_i}
 //
@@ -86,8 +87,12 @@ struct mcb200_layer {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   SoaBuf bank;
   long long n_bank = 0;
-  SoaBuf outbox[2];
+  unsigned long long *d_out[2] = {nullptr, nullptr};      // settled outboxes, 3 words / record
+  long long out_cap[2] = {0, 0};
   long long n_out[2] = {0, 0};
+  unsigned long long *d_scratch[2] = {nullptr, nullptr};  // per-launch stripes + overflow
+  long long scratch_cap[2] = {0, 0};
+  unsigned *d_stripe_n = nullptr;                         // [2][kStripes + 1]
   mcb::CellXs *d_xs = nullptr;
   unsigned *d_acc = nullptr;          // [kAccDigits][m + kAccExtra]
   mcb::DevCounters *d_ctr = nullptr;
@@ -137,6 +142,25 @@ int soa_reserve(mcb200_layer *l, SoaBuf *b, long long used, long long want) {
   b->seed = ns;
   b->st = nt;
   b->cap = cap;
+  return MCB200_OK;
+}
+
+// growable buffer of 24-byte records; the first `used` records survive a growth
+int rec_reserve(mcb200_layer *l, unsigned long long **buf, long long *cap, long long used,
+                long long want) {
+  if (want <= *cap) return MCB200_OK;
+  long long nc = *cap > 0 ? *cap : 4096;
+  while (nc < want) nc += nc / 2 + 1;
+  unsigned long long *nb = nullptr;
+  MCB_CUDA(cudaMalloc(&nb, (size_t)nc * sizeof(mcb200_particle)));
+  if (used > 0) {
+    MCB_CUDA(cudaMemcpyAsync(nb, *buf, (size_t)used * sizeof(mcb200_particle),
+                             cudaMemcpyDeviceToDevice, l->stream));
+    MCB_CUDA(cudaStreamSynchronize(l->stream));
+  }
+  cudaFree(*buf);
+  *buf = nb;
+  *cap = nc;
   return MCB200_OK;
 }
 
@@ -214,16 +238,22 @@ int track(mcb200_layer *l, long long take) {
   }
   const bool write_side[2] = {!l->left_border || l->keep_border,
                               !l->right_border || l->keep_border};
+  // per-CTA stripes: twice the fair share each (dynamic work distribution keeps CTAs within
+  // a few percent of each other), plus one overflow segment that can take everything
+  const int grid = mcb::track_grid(l->cfg, take);
+  const int stripe_cap = (int)(2 * ((take + grid - 1) / grid) + 64);
+  const long long ovf_base = (long long)grid * stripe_cap;
   for (int s = 0; s < 2; ++s) {
     if (!write_side[s]) continue;
-    int rc = soa_reserve(l, &l->outbox[s], l->n_out[s], l->n_out[s] + take);
+    int rc = rec_reserve(l, &l->d_scratch[s], &l->scratch_cap[s], 0, ovf_base + take);
+    if (rc) return rc;
+    rc = rec_reserve(l, &l->d_out[s], &l->out_cap[s], l->n_out[s], l->n_out[s] + take);
     if (rc) return rc;
   }
-  // counters: everything per-launch is zeroed, the outbox fills persist
   std::memset(l->h_ctr, 0, sizeof(mcb::DevCounters));
-  l->h_ctr->out_n[0] = (unsigned long long)l->n_out[0];
-  l->h_ctr->out_n[1] = (unsigned long long)l->n_out[1];
   MCB_CUDA(cudaMemcpyAsync(l->d_ctr, l->h_ctr, sizeof(mcb::DevCounters), cudaMemcpyHostToDevice,
+                           l->stream));
+  MCB_CUDA(cudaMemsetAsync(l->d_stripe_n, 0, 2 * (mcb::kStripes + 1) * sizeof(unsigned),
                            l->stream));
   mcb::TrackParams p{};
   p.bank_seed = l->bank.seed;
@@ -237,15 +267,25 @@ int track(mcb200_layer *l, long long take) {
   p.minw = l->particle_min_weight;
   p.acc = l->d_acc;
   for (int s = 0; s < 2; ++s) {
-    p.out_seed[s] = l->outbox[s].seed;
-    p.out_st[s] = l->outbox[s].st;
-    p.out_cap[s] = l->outbox[s].cap;
+    p.out_rec[s] = l->d_scratch[s];
     p.write_side[s] = write_side[s] ? 1 : 0;
   }
+  p.stripe_n = l->d_stripe_n;
+  p.stripe_cap = stripe_cap;
+  p.ovf_base = ovf_base;
+  p.ovf_cap = take;
   p.ctr = l->d_ctr;
   MCB_CUDA(cudaEventRecord(l->ev0, l->stream));
   MCB_CUDA(mcb::launch_track(p, l->cfg, l->stream));
   MCB_CUDA(cudaEventRecord(l->ev1, l->stream));
+  for (int s = 0; s < 2; ++s) {
+    if (!write_side[s]) continue;
+    MCB_CUDA(mcb::launch_gather_stripes(l->d_scratch[s],
+                                        l->d_stripe_n + s * (mcb::kStripes + 1), grid, stripe_cap,
+                                        ovf_base, l->d_out[s], l->n_out[s],
+                                        &l->d_ctr->out_total[s], l->stream));
+    l->gpu_launches++;
+  }
   MCB_CUDA(cudaMemcpyAsync(l->h_ctr, l->d_ctr, sizeof(mcb::DevCounters), cudaMemcpyDeviceToHost,
                            l->stream));
   // digits of the three class accumulators (weight carried left / right / by the dead)
@@ -273,8 +313,8 @@ int track(mcb200_layer *l, long long take) {
     for (int j = 0; j < mcb::kAccDigits; ++j) d[j] = l->h_cls[j * mcb::kAccExtra + k];
     l->w_cls[k] = acc_to_double(d);  // the device accumulators are cumulative
   }
-  l->n_out[0] = (long long)c.out_n[0];
-  l->n_out[1] = (long long)c.out_n[1];
+  l->n_out[0] += (long long)c.out_total[0];
+  l->n_out[1] += (long long)c.out_total[1];
   // src/layer.cpp:343 (dead) and :350-360 (global borders absorb)
   l->nb_disabled += (long long)c.n_cls[2];
   if (l->left_border) l->nb_disabled += (long long)c.n_cls[0];
@@ -313,18 +353,10 @@ int pop_side(mcb200_layer *l, int side, void *dst, bool dst_is_device, long long
     *n_out = n;
     return fail(MCB200_ERR_CAPACITY, "pop: caller buffer too small");
   }
-  if (n > 0) {
-    void *aos = dst;
-    if (!dst_is_device) {
-      int rc = stage_reserve(l, n);
-      if (rc) return rc;
-      aos = l->d_stage;
-    }
-    MCB_CUDA(mcb::launch_soa_to_aos(n, l->outbox[side].seed, l->outbox[side].st, aos, l->stream));
-    l->gpu_launches++;
-    if (!dst_is_device)
-      MCB_CUDA(cudaMemcpyAsync(dst, aos, (size_t)n * sizeof(mcb200_particle),
-                               cudaMemcpyDeviceToHost, l->stream));
+  if (n > 0) {  // the outbox already holds wire records: one copy
+    MCB_CUDA(cudaMemcpyAsync(dst, l->d_out[side], (size_t)n * sizeof(mcb200_particle),
+                             dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             l->stream));
     MCB_CUDA(cudaStreamSynchronize(l->stream));
   }
   l->n_out[side] = 0;
@@ -433,6 +465,8 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   cuda_ok(cudaMalloc(&l->d_xs, (size_t)l->m * sizeof(mcb::CellXs)), "cudaMalloc xs");
   cuda_ok(cudaMalloc(&l->d_acc, l->acc_words() * sizeof(unsigned)), "cudaMalloc tally");
   cuda_ok(cudaMalloc(&l->d_ctr, sizeof(mcb::DevCounters)), "cudaMalloc counters");
+  cuda_ok(cudaMalloc(&l->d_stripe_n, 2 * (mcb::kStripes + 1) * sizeof(unsigned)),
+          "cudaMalloc stripe fills");
   cuda_ok(cudaMallocHost(&l->h_ctr, sizeof(mcb::DevCounters)), "cudaMallocHost counters");
   cuda_ok(cudaMallocHost(&l->h_cls, mcb::kAccDigits * mcb::kAccExtra * sizeof(unsigned)),
           "cudaMallocHost class weights");
@@ -458,9 +492,10 @@ void mcb200_layer_destroy(mcb200_layer *l) {
     cudaFree(l->bank.seed);
     cudaFree(l->bank.st);
     for (int s = 0; s < 2; ++s) {
-      cudaFree(l->outbox[s].seed);
-      cudaFree(l->outbox[s].st);
+      cudaFree(l->d_out[s]);
+      cudaFree(l->d_scratch[s]);
     }
+    cudaFree(l->d_stripe_n);
     cudaFree(l->d_xs);
     cudaFree(l->d_acc);
     cudaFree(l->d_ctr);
@@ -503,17 +538,21 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
     return code;
   };
   cudaStreamSynchronize(src->stream);
-  const SoaBuf *from[3] = {&src->bank, &src->outbox[0], &src->outbox[1]};
-  SoaBuf *to[3] = {&l->bank, &l->outbox[0], &l->outbox[1]};
-  const long long used[3] = {src->n_bank, src->n_out[0], src->n_out[1]};
-  for (int k = 0; k < 3; ++k) {
-    if (used[k] <= 0) continue;
-    rc = soa_reserve(l, to[k], 0, used[k]);
+  if (src->n_bank > 0) {
+    rc = soa_reserve(l, &l->bank, 0, src->n_bank);
     if (rc) return bail(rc);
-    if (cudaMemcpyAsync(to[k]->seed, from[k]->seed, (size_t)used[k] * 8, cudaMemcpyDeviceToDevice,
-                        l->stream) != cudaSuccess ||
-        cudaMemcpyAsync(to[k]->st, from[k]->st, (size_t)used[k] * 16, cudaMemcpyDeviceToDevice,
-                        l->stream) != cudaSuccess)
+    if (cudaMemcpyAsync(l->bank.seed, src->bank.seed, (size_t)src->n_bank * 8,
+                        cudaMemcpyDeviceToDevice, l->stream) != cudaSuccess ||
+        cudaMemcpyAsync(l->bank.st, src->bank.st, (size_t)src->n_bank * 16,
+                        cudaMemcpyDeviceToDevice, l->stream) != cudaSuccess)
+      return bail(fail(MCB200_ERR_CUDA, "clone: device copy failed"));
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (src->n_out[k] <= 0) continue;
+    rc = rec_reserve(l, &l->d_out[k], &l->out_cap[k], 0, src->n_out[k]);
+    if (rc) return bail(rc);
+    if (cudaMemcpyAsync(l->d_out[k], src->d_out[k], (size_t)src->n_out[k] * sizeof(mcb200_particle),
+                        cudaMemcpyDeviceToDevice, l->stream) != cudaSuccess)
       return bail(fail(MCB200_ERR_CUDA, "clone: device copy failed"));
   }
   if (cudaMemcpyAsync(l->d_acc, src->d_acc, l->acc_words() * sizeof(unsigned),
