@@ -181,6 +181,8 @@ def run_gpu_arm(args):
     if _abi.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -201,6 +203,14 @@ def run_gpu_arm(args):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def per_rank(x: float):
+        if dist is None:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [round(v, 3) for v in t.tolist()]
 
     def sum_over_ranks(x: float) -> float:
         if dist is None:
@@ -274,6 +284,10 @@ def run_gpu_arm(args):
                       "t_exchange_s_max": max_over_ranks(sw.t_exchange),
                       "track_ms_max": max_over_ranks(track_ms),
                       "track_ms_sum": sum_over_ranks(track_ms),
+                      "track_ms_per_rank": per_rank(track_ms),
+                      "events_per_rank": per_rank(float(my_events)),
+                      "segments_per_rank": per_rank(float(
+                          sum(c1[k] - c0[k] for k in ("n_left", "n_right", "n_dead")))),
                       "note": "host wall-clock split of SlabWorld.spin over warm-up + timed steps; "
                               "track_ms = tracking-kernel time of the timed steps"}
 

@@ -167,6 +167,7 @@ void *mcb200_layer_stream(mcb200_layer *l);
 /* tuning knobs; key/value, returns MCB200_ERR_INVALID for unknown keys:
  *   "tally_mode"   0 auto, 1 CTA-private shared-memory tally, 2 global (L2) tally
  *   "block"        threads per CTA,  "blocks_per_sm" CTAs per SM
+ *   "retire_batch" lanes of a warp without a live history before retire/refill runs (0 auto)
  *   "birth_chunk"  max particles born per launch */
 int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value);
 

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
   const int lo = p.idx_lo;
   const int hi = p.idx_lo + p.m;
   const float dx = p.dx, minw = p.minw;
+  const int retire_batch = p.retire_batch;
   const unsigned long long take = (unsigned long long)p.take_count;
 
   // particle state, include/types/particle.hpp:7-18, one history per lane
@@ -169,9 +170,11 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
   for (;;) {
     // ---- liveness: loop condition of simulate_particle, src/layer.cpp:195-197
     const bool alive = active && (wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)p.m);
-    // steady state: all 32 lanes carry a live history -> one vote, straight to the event.
-    // Retire / refill / exit only run on the iterations where some lane is not alive.
-    if (!__all_sync(MCB_FULL, alive)) {
+    // steady state: (almost) all 32 lanes carry a live history -> one vote, straight to the
+    // event.  Retire / refill / exit run only once `retire_batch` lanes are without a live
+    // history (or, at the tail, on every iteration), so that their cost is shared.
+    const unsigned nolive = __ballot_sync(MCB_FULL, !alive);
+    if (nolive != 0u && (__popc(nolive) >= retire_batch || exhausted)) {
     const bool fin = active && !alive;
     const unsigned fm = __ballot_sync(MCB_FULL, fin);
     if (fm) {

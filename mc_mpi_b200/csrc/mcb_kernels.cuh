@@ -72,6 +72,8 @@ struct TrackParams {
   long long ovf_base;    // first record of the overflow segment (= grid * stripe_cap)
   long long ovf_cap;     // its capacity
   int write_side[2];     // 0: global border, escapees are only counted
+  int retire_batch;      // retire / refill once this many lanes of a warp are without a live
+                         // history (>= 1): amortises the bookkeeping over short segments
   DevCounters *ctr;
 };
 

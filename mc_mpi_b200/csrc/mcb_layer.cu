@@ -103,7 +103,7 @@ struct mcb200_layer {
   bool xs_dirty = true;
   mcb::JumpTable seed_jump;
   // --- knobs / cumulative stats
-  int opt_tally_mode = 0, opt_block = 0, opt_bps = 0;
+  int opt_tally_mode = 0, opt_block = 0, opt_bps = 0, opt_retire_batch = 0;
   long long opt_birth_chunk = 1ll << 26;
   bool cfg_dirty = true;
   mcb::TrackLaunch cfg{};
@@ -275,6 +275,9 @@ int track(mcb200_layer *l, long long take) {
   p.ovf_base = ovf_base;
   p.ovf_cap = take;
   p.ctr = l->d_ctr;
+  // short segments (thin sub-slabs of a multi-GPU run) retire often: batch the bookkeeping
+  p.retire_batch = l->opt_retire_batch > 0 ? l->opt_retire_batch : (l->m < 512 ? 4 : 2);
+  if (p.retire_batch > 32) p.retire_batch = 32;
   MCB_CUDA(cudaEventRecord(l->ev0, l->stream));
   MCB_CUDA(mcb::launch_track(p, l->cfg, l->stream));
   MCB_CUDA(cudaEventRecord(l->ev1, l->stream));
@@ -570,6 +573,7 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
   l->opt_tally_mode = src->opt_tally_mode;
   l->opt_block = src->opt_block;
   l->opt_bps = src->opt_bps;
+  l->opt_retire_batch = src->opt_retire_batch;
   l->opt_birth_chunk = src->opt_birth_chunk;
   l->events = src->events;
   l->scatters = src->scatters;
@@ -729,6 +733,7 @@ int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value) {
   if (k == "tally_mode") l->opt_tally_mode = (int)value;
   else if (k == "block") l->opt_block = (int)value;
   else if (k == "blocks_per_sm") l->opt_bps = (int)value;
+  else if (k == "retire_batch") l->opt_retire_batch = (int)value;
   else if (k == "birth_chunk") {
     if (value <= 0) return fail(MCB200_ERR_INVALID, "set_option: birth_chunk must be positive");
     l->opt_birth_chunk = value;

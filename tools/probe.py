@@ -1,5 +1,6 @@
 """Quick device-side throughput sweep of the tracking kernel variants (developer tool).
-usage: python tools/probe.py [particles] [config]"""
+usage: python tools/probe.py [particles] [config] [K rank]   (K rank: track only that sub-slab,
+the workload of one rank of a K-GPU run: births if it owns the source, else nothing)"""
 import json
 import sys
 import time
@@ -17,12 +18,14 @@ shapes = [dict(block=256, blocks_per_sm=4), dict(block=128, blocks_per_sm=8),
           dict(block=512, blocks_per_sm=2), dict(block=1024, blocks_per_sm=1),
           dict(block=256, blocks_per_sm=6), dict(block=256, blocks_per_sm=8),
           dict(block=128, blocks_per_sm=12), dict(block=256, blocks_per_sm=2)]
-if len(sys.argv) > 3:
-    shapes = shapes[:1]
+K, R = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1, 0)
+if K > 1:
+    variants = [dict(tally_mode=1, retire_batch=b) for b in (1, 2, 4, 8, 12)]
+    shapes = shapes[:1] + shapes[4:5]
 for v in variants:
-    for s in (shapes if v == variants[0] else shapes[:1]):
-        g = decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, 1, 0, cfg.nb_cells, cfg.nb_particles,
-                             cfg.particle_min_weight, sigs=cfg.sigs,
+    for s in (shapes if (v == variants[0] or K > 1) else shapes[:1]):
+        g = decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, K, R, cfg.nb_cells, cfg.nb_particles,
+                             cfg.particle_min_weight, sigs=cfg.sigs, global_dx=K > 1,
                              absorption_rates=cfg.absorption_rates)
         for k, val in {**v, **s}.items():
             g.set_option(k, val)
@@ -33,6 +36,7 @@ for v in variants:
             t = time.time()
             c = g.simulate(-1)
             wall = time.time() - t
+            g.pop_left(), g.pop_right()
             ms = c["track_ms"] - c0["track_ms"]
             ev = c["events"] - c0["events"]
             if best is None or ms < best[0]:
