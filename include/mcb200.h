@@ -120,7 +120,8 @@ int mcb200_layer_create_particles(mcb200_layer *l, float x_ini, float wmc,
 /* append n host particles to the bank -- what the workers do on receive
  * (src/worker_sync.cpp:47-108, src/async_comm.cpp:140-143, src/rma_comm.cpp:210) */
 int mcb200_layer_push(mcb200_layer *l, const mcb200_particle *aos, int64_t n);
-/* same, from DEVICE memory on the layer's GPU (24-byte records) */
+/* same, from DEVICE memory on the layer's GPU (24-byte records).  Asynchronous: the
+ * source must stay untouched until the next simulate() / pop on this layer. */
 int mcb200_layer_push_device(mcb200_layer *l, const void *dev_aos, int64_t n);
 
 /* ---- the hot path ----------------------------------------------------- */
@@ -146,6 +147,12 @@ int mcb200_layer_pop_left_device(mcb200_layer *l, void *dev_aos, int64_t cap,
                                  int64_t *n_out);
 int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap,
                                   int64_t *n_out);
+/* zero-copy variant for a device-side exchange: the outbox itself (side 0 = left,
+ * 1 = right) as `*n_out` contiguous 24-byte records in device memory, valid until the
+ * next simulate() on this layer; mcb200_layer_outbox_clear() empties it once shipped. */
+int mcb200_layer_outbox_device(mcb200_layer *l, int32_t side, void **dev_aos_out,
+                               int64_t *n_out);
+int mcb200_layer_outbox_clear(mcb200_layer *l, int32_t side);
 /* weights_absorbed (layer.hpp:92), m entries.  The device keeps every cell as
  * an EXACT 128-bit fixed-point sum of the per-event float deposits (order-,
  * launch- and GPU-count-independent).  _exact returns it: four little-endian

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcb200.so")
+LIB_PATH = os.environ.get("MCB200_LIB") or os.path.join(HERE, "libmcb200.so")
 
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_RANGE = 0, -1, -2, -3, -4, -5
@@ -73,6 +73,8 @@ SYMBOLS = {
     "mcb200_layer_pop_right": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
     "mcb200_layer_pop_left_device": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
     "mcb200_layer_pop_right_device": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
+    "mcb200_layer_outbox_device": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_I64)]),
+    "mcb200_layer_outbox_clear": (C.c_int, [_P, _I32]),
     "mcb200_layer_weights_absorbed": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_f64": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_exact": (C.c_int, [_P, _P, C.POINTER(_I32)]),

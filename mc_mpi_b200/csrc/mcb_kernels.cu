@@ -97,6 +97,34 @@ __device__ __forceinline__ void acc_add(unsigned *w, int stride, float v, unsign
   }
 }
 
+// The same deposit into a CTA-private accumulator in SHARED memory, addressed by its
+// 32-bit shared-window byte address (`w` = digit 0 of the cell, `stride` bytes between
+// digits) with explicit atom.shared -- see mcb_math.cuh on why not generic pointers.
+__device__ __forceinline__ void acc_add_smem(unsigned w, unsigned stride, float v,
+                                             unsigned *range_flag) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned pos = (b >> 23) - (unsigned)(150 + kAccLsbLog2);
+  if (pos <= (unsigned)(32 * kAccDigits - 25)) {
+    const unsigned mant = (b & 0x7fffffu) | 0x800000u;
+    const unsigned j = pos >> 5;
+    const unsigned o = pos & 31u;
+    const unsigned lo = mant << o;
+    const unsigned hi = __funnelshift_l(mant, 0u, o);
+    const unsigned d = w + j * stride;
+    const unsigned old = atoms_add_u32(d, lo);
+    const unsigned c = hi + (old > ~lo ? 1u : 0u);
+    if (c != 0u && j < (unsigned)(kAccDigits - 1)) {
+      const unsigned old2 = atoms_add_u32(d + stride, c);
+      if (old2 > ~c)
+        acc_ripple(static_cast<unsigned *>(__cvta_shared_to_generic(w)), (int)(stride >> 2),
+                   (int)j + 2);
+    }
+  } else {
+    acc_add_slow(static_cast<unsigned *>(__cvta_shared_to_generic(w)), (int)(stride >> 2), v,
+                 range_flag);
+  }
+}
+
 // add a whole accumulator (digits d[0..3] of one cell) into another one
 __device__ __forceinline__ void acc_merge(unsigned *w, int stride, const unsigned d[kAccDigits]) {
   unsigned c = 0u;
@@ -127,11 +155,14 @@ struct TrackSmem {
 // ----------------------------------------------------------- the hot path --
 
 // MAXB = largest CTA this instantiation is launched with.  The 256-thread one is the
-// workhorse: 6 CTAs per SM (1536 resident threads) caps it at 40 registers, which is what
-// the event loop needs; the 1024-thread one exists for sub-slabs whose CTA-private tally
+// workhorse: 4 CTAs per SM (1024 resident threads, <= 64 registers).  Measured on B200
+// (tools/quick_variants.py): a 40-register cap (6 CTAs/SM) makes ptxas re-materialise
+// addresses and constants inside the event loop and is 5 % slower (1.80e11 vs 1.89e11
+// events/s); the kernel is issue-bound with ~5 eligible warps per issue slot, so the extra
+// occupancy buys nothing.  The 1024-thread one exists for sub-slabs whose CTA-private tally
 // only fits once per SM.
 template <bool SHARED, int MAXB>
-__global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const TrackParams p) {
+__global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const TrackParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem *sm = reinterpret_cast<TrackSmem *>(smem_raw);
   CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(TrackSmem));
@@ -148,6 +179,12 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
     for (int c = threadIdx.x; c < kAccDigits * ncell; c += blockDim.x) acc[c] = 0u;
   }
   __syncthreads();
+
+  // 32-bit shared-window addresses of the three shared structures the event touches
+  const unsigned tb_s = smem_addr(&sm->math);
+  const unsigned xs_s = smem_addr(s_xs);
+  const unsigned acc_s = smem_addr(s_xs + p.m);
+  const unsigned acc_stride = (unsigned)ncell * 4u;  // bytes between digits
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -181,7 +218,11 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
       // ---- retire: classification of src/layer.cpp:202-217, routing of
       // :332-346, global-border absorption of :350-360
       const int cls = (idx == lo - 1) ? 0 : (idx == hi) ? 1 : (wmc < minw) ? 2 : 0;
-      if (fin) acc_add(&acc[p.m + cls], ncell, wmc, &p.ctr->acc_range);
+      if (fin) {
+        if (SHARED) acc_add_smem(acc_s + (unsigned)(p.m + cls) * 4u, acc_stride, wmc,
+                                 &p.ctr->acc_range);
+        else acc_add(&p.acc[p.m + cls], ncell, wmc, &p.ctr->acc_range);
+      }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const bool mine = fin && cls == c;
@@ -257,11 +298,12 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
       const int il = idx - lo;                                   // :129
-      const CellXs xs = SHARED ? s_xs[il] : __ldg(&p.xs[il]);    // :131-133
+      const CellXs xs = SHARED ? lds_f32x2(xs_s + (unsigned)il * 8u)
+                               : __ldg(&p.xs[il]);               // :131-133
       seed = lcg_next(seed);                                     // :136
       const float h = lcg_to_real(seed);
       float di = MCB_MAXREAL;                                    // :137
-      if (xs.y > MCB_EPS) di = __fdiv_rn(-logf_glibc(h, &sm->math), xs.y);
+      if (xs.y > MCB_EPS) di = __fdiv_rn(-logf_glibc(h, tb_s), xs.y);
 
       const bool neg = mu < 0.0f;                                // :143-152
       int inew = neg ? idx - 1 : idx + 1;
@@ -279,10 +321,12 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 6 : 1) track_kernel(const 
         di = de;
         x = xe;
       }
-      const float e = expf_glibc_nonpos(__fmul_rn(-xs.x, di), &sm->math);
+      const float e = expf_glibc_nonpos(__fmul_rn(-xs.x, di), tb_s);
       const float dw = __fmul_rn(__fsub_rn(1.0f, e), wmc);       // :175
       wmc = __fsub_rn(wmc, dw);                                  // :178
-      acc_add(&acc[il], ncell, dw, &p.ctr->acc_range);           // :179, exactly
+      // :179, exactly
+      if (SHARED) acc_add_smem(acc_s + (unsigned)il * 4u, acc_stride, dw, &p.ctr->acc_range);
+      else acc_add(&p.acc[il], ncell, dw, &p.ctr->acc_range);
       idx = inew;                                                // :181
       ++n_ev;
     }
@@ -355,7 +399,7 @@ cudaError_t track_configure(int device, int m, int want_mode, int want_block,
   // CTA shape: as many resident threads as the register file allows, in CTAs
   // small enough that their private tally copies fit side by side
   int block = want_block > 0 ? want_block : 256;
-  int bps = want_blocks_per_sm > 0 ? want_blocks_per_sm : 1536 / block;
+  int bps = want_blocks_per_sm > 0 ? want_blocks_per_sm : 1024 / block;
   if (want_block <= 0 && want_blocks_per_sm <= 0) {
     while (bps > 1 && (smem + reserve) * (size_t)bps > per_sm) {
       bps /= 2;
@@ -539,12 +583,13 @@ cudaError_t launch_test_rnd_real(long long n, unsigned long long *seeds, float *
 }
 
 __global__ void test_math_kernel(int which, long long n, const float *in, float *out) {
-  __shared__ MathTables tb;
-  load_math_tables(&tb);
+  __shared__ MathTables tb_smem;
+  load_math_tables(&tb_smem);
   __syncthreads();
+  const unsigned tb = smem_addr(&tb_smem);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = which == 0 ? logf_glibc(in[i], &tb) : expf_glibc_nonpos(in[i], &tb);
+    out[i] = which == 0 ? logf_glibc(in[i], tb) : expf_glibc_nonpos(in[i], tb);
 }
 
 cudaError_t launch_test_math(int which, long long n, const float *in, float *out,
@@ -563,7 +608,7 @@ __global__ void test_accumulate_kernel(long long n, const float *in, unsigned *a
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    acc_add(s_acc, 1, in[i], range_flag);
+    acc_add_smem(smem_addr(s_acc), 4u, in[i], range_flag);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned d[kAccDigits];

@@ -384,8 +384,10 @@ int push_any(mcb200_layer *l, const void *src, bool src_is_device, long long n) 
   MCB_CUDA(mcb::launch_aos_to_soa(n, aos, l->bank.seed + l->n_bank, l->bank.st + l->n_bank,
                                   l->stream));
   l->gpu_launches++;
-  // the staging buffer / caller buffer may be reused as soon as we return
-  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  // a host source (and the staging buffer) may be reused as soon as we return; a DEVICE
+  // source only has to stay untouched until the next blocking call on this layer
+  // (simulate / pop / counts), which lets an exchange queue both neighbours' records
+  if (!src_is_device) MCB_CUDA(cudaStreamSynchronize(l->stream));
   l->n_bank += n;
   return MCB200_OK;
 }
@@ -677,6 +679,20 @@ int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap, i
   int rc = pop_side(l, 1, dev_aos, true, cap, &n);
   if (n_out) *n_out = n;
   return rc;
+}
+
+int mcb200_layer_outbox_device(mcb200_layer *l, int32_t side, void **dev_aos_out, int64_t *n_out) {
+  if (!l || side < 0 || side > 1 || !dev_aos_out || !n_out)
+    return fail(MCB200_ERR_INVALID, "outbox_device: bad argument");
+  *dev_aos_out = l->d_out[side];
+  *n_out = l->n_out[side];
+  return MCB200_OK;
+}
+
+int mcb200_layer_outbox_clear(mcb200_layer *l, int32_t side) {
+  if (!l || side < 0 || side > 1) return fail(MCB200_ERR_INVALID, "outbox_clear: bad argument");
+  l->n_out[side] = 0;
+  return MCB200_OK;
 }
 
 int mcb200_layer_weights_absorbed_exact(mcb200_layer *l, uint32_t *out_4m, int32_t *lsb_log2) {

@@ -91,6 +91,35 @@ __device__ __forceinline__ void load_math_tables(MathTables *s) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+// ---- explicit shared-memory accesses ----------------------------------------
+// The hot loop addresses shared memory with 32-bit shared-window offsets kept in
+// a register and explicit ld.shared / atom.shared: going through generic
+// pointers makes ptxas re-derive the window base (S2R SR_CgaCtaId + LEA) at every
+// use once registers are capped at 40.
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float2 lds_f32x2(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(unsigned addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned atoms_add_u32(unsigned addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
 // ---- LCG ------------------------------------------------------------------
 // one step of the rnd_real stream, src/random.cpp:14 ((G*s + C) % 2^63)
 __device__ __forceinline__ uint64_t lcg_next(uint64_t s) {
@@ -145,7 +174,8 @@ __host__ __device__ inline uint64_t jump_state(const JumpTable &t, uint64_t k, u
 // ---- logf -----------------------------------------------------------------
 // glibc sysdeps/ieee754/flt-32/e_logf.c (LOGF_TABLE_BITS 4, POLY_ORDER 4).
 // Domain on the path: h = rnd_real() in {+0} U [2^-63, 1] (src/layer.cpp:136).
-__device__ __forceinline__ float logf_glibc(float x, const MathTables *tb) {
+// `tb` = smem_addr() of the CTA's MathTables copy.
+__device__ __forceinline__ float logf_glibc(float x, unsigned tb) {
   const double ln2 = c_mc.ln2, a0 = c_mc.a0, a1 = c_mc.a1, a2 = c_mc.a2;
   const uint32_t ix = __float_as_uint(x);
   const uint32_t tmp = ix - 0x3f330000u;
@@ -155,7 +185,7 @@ __device__ __forceinline__ float logf_glibc(float x, const MathTables *tb) {
   // (double)asfloat(iz): iz is a positive normal float in [0.7, 1.4), so the
   // widening is an exponent re-bias and a mantissa shift
   const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
-  const double2 t = tb->log_tab[i];
+  const double2 t = lds_f64x2(tb + i * 16u);  // MathTables::log_tab[i]
   const double r = __fma_rn(z, t.x, -1.0);
   const double y0 = __fma_rn((double)k, ln2, t.y);
   const double r2 = __dmul_rn(r, r);
@@ -172,7 +202,7 @@ __device__ __forceinline__ float logf_glibc(float x, const MathTables *tb) {
 // glibc sysdeps/ieee754/flt-32/e_expf.c (EXP2F_TABLE_BITS 5).  Domain on the
 // path: -sig_a*di in [-inf, +0] (src/layer.cpp:175); the result only enters
 // as 1 - expf().
-__device__ __forceinline__ float expf_glibc_nonpos(float x, const MathTables *tb) {
+__device__ __forceinline__ float expf_glibc_nonpos(float x, unsigned tb) {
   const double shift = c_mc.shift, inv_ln2_n = c_mc.inv_ln2_n;
   const double c0 = c_mc.c0, c1 = c_mc.c1, c2 = c_mc.c2;
   const uint32_t ix = __float_as_uint(x);
@@ -187,7 +217,8 @@ __device__ __forceinline__ float expf_glibc_nonpos(float x, const MathTables *tb
   kd = __dsub_rn(kd, shift);
   const double r = __dsub_rn(z, kd);
   // t = T[ki % 32] + (ki << 47): only the high word changes
-  const unsigned long long t0 = tb->exp_tab[ki & 31u];
+  const unsigned long long t0 =
+      lds_u64(tb + (unsigned)sizeof(double2) * 16u + (ki & 31u) * 8u);  // MathTables::exp_tab
   const double s = __hiloint2double((int)((uint32_t)(t0 >> 32) + (ki << 15)),
                                     (int)(uint32_t)t0);
   const double zz = __fma_rn(c0, r, c1);

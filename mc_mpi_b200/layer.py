@@ -131,6 +131,16 @@ class Layer:
         check(fn(self._h, C.c_void_p(dev_ptr), int(cap), C.byref(got)))
         return got.value
 
+    def outbox_device(self, side: int):
+        """(device pointer, n): the outbox itself, n contiguous 24-byte records (zero-copy;
+        valid until the next simulate())."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        check(_abi.lib().mcb200_layer_outbox_device(self._h, int(side), C.byref(ptr), C.byref(n)))
+        return int(ptr.value or 0), n.value
+
+    def outbox_clear(self, side: int):
+        check(_abi.lib().mcb200_layer_outbox_clear(self._h, int(side)))
+
     @property
     def weights_absorbed(self) -> np.ndarray:
         out = np.empty(self.m, dtype=np.float32)

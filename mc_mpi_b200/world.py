@@ -30,6 +30,14 @@ from .layer import PARTICLE_DTYPE, Layer, decompose_domain, split_cells
 RECORD = PARTICLE_DTYPE.itemsize  # 24 bytes on the wire
 
 
+class _DeviceBytes:
+    """a raw device allocation exposed to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+
+
 class SlabWorld:
     def __init__(self, cfg: _configs.SlabConfig, *, rank=None, world_size=None, device=None,
                  nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True):
@@ -80,10 +88,13 @@ class SlabWorld:
             peer = r + d
             if 0 <= peer < K:
                 if n_send[d] > 0:
-                    sb = self._buffer(f"send{d}", n_send[d])
                     if self.on_device:
-                        got = self.layer.pop_device(side, sb.data_ptr(), n_send[d])
+                        # zero-copy: NCCL reads the layer's outbox (already wire records)
+                        ptr, got = self.layer.outbox_device(side)
+                        sb = torch.as_tensor(_DeviceBytes(ptr, got * RECORD), device=self.tdev)
+                        self.layer.outbox_clear(side)
                     else:
+                        sb = self._buffer(f"send{d}", n_send[d])
                         arr = self.layer.pop_left() if side == 0 else self.layer.pop_right()
                         got = len(arr)
                         sb[: got * RECORD] = torch.from_numpy(
