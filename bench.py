@@ -224,7 +224,6 @@ def run_gpu_arm(args):
         layer = decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, 1, 0, cfg.nb_cells, n_hist,
                                  cfg.particle_min_weight, device=local_rank, sigs=cfg.sigs,
                                  absorption_rates=cfg.absorption_rates)
-        stream = torch.cuda.ExternalStream(layer.stream_ptr, device=torch.device("cuda", local_rank))
 
         def step():
             layer.create_particles(cfg.x_ini, wmc, n_hist)
@@ -232,22 +231,35 @@ def run_gpu_arm(args):
             assert c["nb_active"] == 0
             return c
     else:
-        from mc_mpi_b200.world import SlabWorld
-        sw = SlabWorld(cfg, device=local_rank, nb_particles_per_cycle=args.per_cycle)
+        from mc_mpi_b200.world import SlabWorld, balanced_cuts
+        sw = SlabWorld(cfg, device=local_rank, nb_particles_per_cycle=args.per_cycle,
+                       ramp_from=args.ramp_from if args.ramp_from > 0 else None)
         layer = sw.layer
-        stream = torch.cuda.ExternalStream(layer.stream_ptr, device=torch.device("cuda", local_rank))
-        src = layer.counts()["n_unborn"] > 0
 
         def step():
-            if src:
-                layer.create_particles(cfg.x_ini, wmc, n_hist)
-            base = sum_over_ranks(float(layer.counts()["nb_disabled"]))
+            lay = sw.layer
+            if lay.counts()["n_unborn"] > 0 or lay.index_start <= cell_ini < lay.index_start + lay.m:
+                lay.create_particles(cfg.x_ini, wmc, n_hist)
+            base = sum_over_ranks(float(lay.counts()["nb_disabled"]))
             sw.cfg = cfg.with_particles(int(base) + n_hist)  # disabled counts are cumulative
             sw.spin()
-            return layer.counts()
+            return lay.counts()
 
-    for _ in range(args.warmup):
+        cell_ini = int(np.float32(np.float32(cfg.x_ini) - np.float32(cfg.x_min)) /
+                       (np.float32(np.float32(cfg.x_max) - np.float32(cfg.x_min)) / np.float32(cfg.nb_cells)))
+
+    for w in range(args.warmup):
+        before = sw.layer.counts()["track_ms"] if world > 1 else 0.0
         step()
+        if world > 1 and args.balance and w < args.warmup - 1:
+            # measured load balancing: move the cuts so that every GPU gets the same tracking
+            # time (results do not depend on the cuts: global dx + global cross-section table)
+            cost = per_rank(sw.layer.counts()["track_ms"] - before)
+            sw.cfg = cfg
+            sw.recut(balanced_cuts(sw.cuts, cost, cfg.nb_cells))
+    if world > 1:
+        layer = sw.layer
+    stream = torch.cuda.ExternalStream(layer.stream_ptr, device=torch.device("cuda", local_rank))
     barrier()
     c0 = layer.counts()
     sampler = ClockSampler(local_rank)
@@ -288,6 +300,8 @@ def run_gpu_arm(args):
                       "events_per_rank": per_rank(float(my_events)),
                       "segments_per_rank": per_rank(float(
                           sum(c1[k] - c0[k] for k in ("n_left", "n_right", "n_dead")))),
+                      "cuts": sw.cuts, "balanced": bool(args.balance and args.warmup > 1),
+                      "ramp_from": args.ramp_from,
                       "note": "host wall-clock split of SlabWorld.spin over warm-up + timed steps; "
                               "track_ms = tracking-kernel time of the timed steps"}
 
@@ -358,8 +372,9 @@ def run_gpu_arm(args):
                        "l2_policy": "inputs larger than L2: the source bank is "
                                     f"{n_hist * 24 / 1e9:.1f} GB of particle state per step",
                        "parallelism": "1 GPU" if world == 1 else
-                                      f"domain decomposition, {world} sub-slabs, "
-                                      f"{args.per_cycle} histories per cycle"},
+                                      f"domain decomposition, {world} sub-slabs "
+                                      f"({'cuts balanced on measured tracking time' if args.balance and args.warmup > 1 else 'equal cell counts'}), "
+                                      f"<= {args.per_cycle} source histories per cycle"},
             "events_per_s": events / (dev_ms * 1e-3),
             "wall_s": wall,
             "roofline": {"bound": "hbm", "achieved": achieved_min, "peak": peak, "unit": "GB/s",
@@ -383,7 +398,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["mcb200", "reference"], default="mcb200")
     ap.add_argument("--particles", type=int, default=None, help="histories per step (override)")
-    ap.add_argument("--per-cycle", type=int, default=1 << 23, dest="per_cycle")
+    ap.add_argument("--per-cycle", type=int, default=1 << 24, dest="per_cycle")
+    ap.add_argument("--ramp-from", type=int, default=1 << 20, dest="ramp_from",
+                    help="source histories of the first cycle (doubling up to --per-cycle); 0 = flat")
+    ap.add_argument("--no-balance", action="store_false", dest="balance",
+                    help="keep the reference's equal-cell-count decomposition")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, dest="cpu_sample")
     ap.add_argument("--e2e-particles", type=int, default=HISTORIES_1GPU, dest="e2e_particles")
     ap.add_argument("--no-e2e", action="store_true")

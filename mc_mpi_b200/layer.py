@@ -215,16 +215,20 @@ def split_cells(nb_cells: int, world_size: int, world_rank: int):
 
 def decompose_domain(x_min, x_max, x_ini, world_size, world_rank, nb_cells, nb_particles,
                      particle_min_weight, *, device=0, global_dx=False, keep_border=False,
-                     sigs=None, absorption_rates=None, seed=SEED0) -> Layer:
+                     sigs=None, absorption_rates=None, seed=SEED0, cells=None) -> Layer:
     """decompose_domain, src/layer.cpp:17-42, float arithmetic mirrored in float32.
 
     global_dx=False reproduces the reference (every layer recomputes its own dx
     from its rounded bounds, :47); global_dx=True tracks every sub-slab with the
     one global dx so that K GPUs give the single-GPU trajectories bit for bit.
     `sigs` / `absorption_rates`, if given, are GLOBAL tables (nb_cells entries).
+    `cells` = (start_index, nb_my_cells) overrides the reference's equal split
+    (:24-27) -- with global_dx the result does not depend on where the cuts are,
+    so a driver may place them where the work balances.
     """
     x_min, x_max, x_ini = f32(x_min), f32(x_max), f32(x_ini)
-    start_index, nb_my_cells = split_cells(nb_cells, world_size, world_rank)
+    start_index, nb_my_cells = (split_cells(nb_cells, world_size, world_rank) if cells is None
+                                else (int(cells[0]), int(cells[1])))
     dx = f32(x_max - x_min) / f32(nb_cells)                      # :29
     cell_ini = int(f32(x_ini - x_min) / dx)                      # :30
     lo = f32(x_min + f32(start_index) * dx)                      # :32

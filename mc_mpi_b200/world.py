@@ -38,19 +38,49 @@ class _DeviceBytes:
                                          "data": (int(ptr), False), "version": 2}
 
 
+def equal_cuts(nb_cells: int, world_size: int):
+    """the reference's split (src/layer.cpp:24-27) as K+1 cell boundaries"""
+    return [split_cells(nb_cells, world_size, r)[0] for r in range(world_size)] + [nb_cells]
+
+
+def balanced_cuts(cuts, cost_per_rank, nb_cells, min_cells=8):
+    """New cell boundaries that equalise the measured cost, taking the cost density as
+    uniform inside each current sub-slab.  With the global dx / global cross-section table
+    the RESULT of a run does not depend on the cuts (bit for bit), so they are free to go
+    where the measured work balances; the reference's equal split leaves the sub-slab that
+    holds the source with ~18 % more events than the mean on the default slab."""
+    K = len(cuts) - 1
+    dens = np.concatenate([np.full(cuts[r + 1] - cuts[r], cost_per_rank[r] / (cuts[r + 1] - cuts[r]))
+                           for r in range(K)])
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
+    new = [0]
+    for r in range(1, K):
+        c = int(np.searchsorted(cum, cum[-1] * r / K))
+        c = max(new[-1] + min_cells, min(c, nb_cells - (K - r) * min_cells))
+        new.append(c)
+    return new + [nb_cells]
+
+
 class SlabWorld:
     def __init__(self, cfg: _configs.SlabConfig, *, rank=None, world_size=None, device=None,
-                 nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True):
+                 nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True,
+                 cuts=None, ramp_from=None):
         self.cfg = cfg
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.per_cycle = int(nb_particles_per_cycle)
+        # births per cycle ramp up from `ramp_from` (doubling) and down again at the end, so
+        # that filling / draining the K-stage pipeline costs small cycles, not full ones
+        self.ramp_from = int(ramp_from) if ramp_from else None
+        self.cuts = list(cuts) if cuts is not None else equal_cuts(cfg.nb_cells, self.world_size)
+        if cuts is not None and not global_dx:
+            raise ValueError("custom cuts need global_dx (the reference's per-layer dx depends "
+                             "on the cuts)")
+        self.device = device or 0
+        self.global_dx = global_dx
         if layer is None:
-            layer = decompose_domain(
-                cfg.x_min, cfg.x_max, cfg.x_ini, self.world_size, self.rank, cfg.nb_cells,
-                cfg.nb_particles, cfg.particle_min_weight, device=device or 0,
-                global_dx=global_dx, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
+            layer = self._make_layer()
         self.layer = layer
         # device-resident exchange when the layer lives on a GPU and the backend can move
         # device memory; host staging otherwise (gloo tests)
@@ -60,6 +90,21 @@ class SlabWorld:
         self.cycles = 0
         self.migrations_out = 0
         self.t_simulate = self.t_exchange = 0.0
+
+    def _make_layer(self):
+        cfg = self.cfg
+        lo, hi = self.cuts[self.rank], self.cuts[self.rank + 1]
+        return decompose_domain(
+            cfg.x_min, cfg.x_max, cfg.x_ini, self.world_size, self.rank, cfg.nb_cells,
+            cfg.nb_particles, cfg.particle_min_weight, device=self.device,
+            global_dx=self.global_dx, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates,
+            cells=(lo, hi - lo) if self.global_dx else None)
+
+    def recut(self, cuts):
+        """move the sub-slab boundaries (between runs: the layer is rebuilt, tallies reset)"""
+        self.cuts = list(cuts)
+        self.layer.close()
+        self.layer = self._make_layer()
 
     # -- buffers ---------------------------------------------------------------------
     def _buffer(self, name: str, n_records: int) -> torch.Tensor:
@@ -127,9 +172,18 @@ class SlabWorld:
     def spin(self, max_cycles=10_000_000) -> dict:
         """Worker::spin: cycle until every source particle is disabled somewhere."""
         total = self.cfg.nb_particles
+        births = min(self.ramp_from, self.per_cycle) if self.ramp_from else self.per_cycle
         while self.cycles < max_cycles:
             t0 = time.perf_counter()
-            c = self.layer.simulate(self.per_cycle)
+            if self.ramp_from:
+                # everything received so far + this cycle's share of the source
+                st = self.layer.counts()
+                unborn = st["n_unborn"]
+                b = min(births, max(unborn // 2, self.ramp_from)) if unborn > 0 else 0
+                c = self.layer.simulate(st["n_bank"] + b)
+                births = min(births * 2, self.per_cycle)
+            else:
+                c = self.layer.simulate(self.per_cycle)
             t1 = time.perf_counter()
             disabled = self._exchange(c)
             t2 = time.perf_counter()

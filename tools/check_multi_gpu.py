@@ -24,7 +24,15 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, K = dist.get_rank(), dist.get_world_size()
     cfg = configs.BY_NAME[name]().with_particles(n)
-    w = SlabWorld(cfg, device=local, nb_particles_per_cycle=per_cycle)
+    cuts = None
+    if len(sys.argv) > 4 and sys.argv[4] == "uneven":
+        # deliberately unequal sub-slabs + ramped source schedule: same bits expected
+        wts = np.array([1.0 + 0.35 * ((3 * r) % 5 - 2) / 2 for r in range(K)])
+        edges = np.concatenate([[0], np.cumsum(wts / wts.sum() * cfg.nb_cells)]).round().astype(int)
+        edges[-1] = cfg.nb_cells
+        cuts = edges.tolist()
+    w = SlabWorld(cfg, device=local, nb_particles_per_cycle=per_cycle, cuts=cuts,
+                  ramp_from=(per_cycle // 8 or 1) if cuts else None)
     s = w.spin()
     wa = w.gather_weights_absorbed()
     stats = torch.tensor([s["events"], s["scatters"], s["migrations_out"],
@@ -48,6 +56,7 @@ def main():
                   "max rel", float(np.max(np.abs(w1 - wa) / w1)) if len(bad) else 0.0,
                   "sum K", float(wa.sum()), "sum 1", float(w1.sum()))
         ok &= same_counts
+        print(f"[multi-gpu parity] cuts={w.cuts}")
         print(f"[multi-gpu parity] K={K} config={cfg.name} histories={n} cycles={s['cycles']} "
               f"migrations/history={mig / n:.3f} events={ev} tally_bit_exact={ok}", flush=True)
         one.close()
