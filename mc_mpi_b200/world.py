@@ -7,12 +7,17 @@ plumbing (NCCL over NVLink on GPUs, gloo on CPU for the host-logic tests).  The 
 topology is the reference's: rank r only ever talks to r-1 and r+1.
 
 What is different from the MPI workers:
-  * escapees never touch the host: the tracking kernel compacts them into device outboxes,
-    `pop_*_device` packs the 24-byte wire records into the send buffer, NCCL moves them
-    GPU-to-GPU, `push_device` unpacks them into the neighbour's bank;
-  * every sub-slab tracks with the ONE global dx (decompose_domain(global_dx=True)), so a
-    K-GPU run reproduces the 1-GPU trajectories bit for bit (the reference's K-rank runs
-    differ from its 1-rank run by up to 5e-4 per cell, SURVEY hard part 3);
+  * escapees never touch the host: the tracking kernel compacts them into device outboxes
+    of 24-byte wire records, NCCL moves them GPU-to-GPU, `push_device` unpacks them into
+    the neighbour's bank;
+  * the exchange of cycle c is IN FLIGHT while cycle c+1 is being tracked (the async
+    worker's idea, src/worker_async.cpp, without its polling): per cycle the cost is
+    max(track, transfer) instead of their sum;
+  * every sub-slab tracks with the ONE global dx and slices of the ONE global cross-section
+    table (decompose_domain(global_dx=True)), so a K-GPU run reproduces the 1-GPU run bit
+    for bit wherever the cuts are (the reference's K-rank runs differ from its 1-rank run
+    by up to 5e-4 per cell, SURVEY hard part 3) -- which frees the cuts to be placed where
+    the measured work balances (`balanced_cuts`);
   * the per-cycle bookkeeping (outbox sizes + disabled counts) is ONE small all-gather
     instead of 4 Sendrecv + Barrier + Allreduce (src/worker_sync.cpp:47-120).
 """
@@ -28,14 +33,6 @@ from . import configs as _configs
 from .layer import PARTICLE_DTYPE, Layer, decompose_domain, split_cells
 
 RECORD = PARTICLE_DTYPE.itemsize  # 24 bytes on the wire
-
-
-class _DeviceBytes:
-    """a raw device allocation exposed to torch through __cuda_array_interface__"""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
-                                         "data": (int(ptr), False), "version": 2}
 
 
 def equal_cuts(nb_cells: int, world_size: int):
@@ -64,7 +61,7 @@ def balanced_cuts(cuts, cost_per_rank, nb_cells, min_cells=8):
 class SlabWorld:
     def __init__(self, cfg: _configs.SlabConfig, *, rank=None, world_size=None, device=None,
                  nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True,
-                 cuts=None, ramp_from=None):
+                 cuts=None, ramp_from=None, overlap=True):
         self.cfg = cfg
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -86,6 +83,7 @@ class SlabWorld:
         # device memory; host staging otherwise (gloo tests)
         self.on_device = isinstance(layer, Layer) and dist.get_backend(group) == "nccl"
         self.tdev = torch.device("cuda", layer.device) if self.on_device else torch.device("cpu")
+        self.overlap = bool(overlap)
         self._buf = {}
         self.cycles = 0
         self.migrations_out = 0
@@ -115,64 +113,74 @@ class SlabWorld:
             self._buf[name] = b
         return b
 
+    def _global(self, group_rank: int) -> int:
+        return dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+
     # -- one cycle -------------------------------------------------------------------
-    def _exchange(self, counts: dict):
-        """ship particles_left / particles_right to rank-1 / rank+1, receive theirs
-        (src/worker_sync.cpp:47-108), return the global disabled count (:112-120)."""
-        K, r = self.world_size, self.rank
+    def _gather_counts(self, counts: dict) -> torch.Tensor:
+        """[K, 3] table of (outbox left, outbox right, nb_disabled): replaces the sizes the
+        MPI workers learn from MPI_Get_count and the Allreduce of src/worker_sync.cpp:112-120"""
+        K = self.world_size
         mine = torch.tensor([counts["n_outbox_left"], counts["n_outbox_right"],
                              counts["nb_disabled"]], dtype=torch.int64, device=self.tdev)
         table = torch.empty(K * 3, dtype=torch.int64, device=self.tdev)
         dist.all_gather_into_tensor(table, mine, group=self.group)
-        table = table.view(K, 3).cpu()
+        return table.view(K, 3).cpu()
+
+    def _start_exchange(self, table: torch.Tensor, parity: int):
+        """post the sends of particles_left / particles_right to rank-1 / rank+1 and the
+        matching receives (src/worker_sync.cpp:47-108); returns what _finish_exchange needs"""
+        K, r = self.world_size, self.rank
         n_send = {-1: int(table[r, 0]), +1: int(table[r, 1])}
         n_recv = {-1: int(table[r - 1, 1]) if r > 0 else 0,
                   +1: int(table[r + 1, 0]) if r + 1 < K else 0}
         ops, recv_bufs = [], {}
         for side, d in ((0, -1), (1, +1)):
             peer = r + d
-            if 0 <= peer < K:
-                if n_send[d] > 0:
-                    if self.on_device:
-                        # zero-copy: NCCL reads the layer's outbox (already wire records)
-                        ptr, got = self.layer.outbox_device(side)
-                        sb = torch.as_tensor(_DeviceBytes(ptr, got * RECORD), device=self.tdev)
-                        self.layer.outbox_clear(side)
-                    else:
-                        sb = self._buffer(f"send{d}", n_send[d])
-                        arr = self.layer.pop_left() if side == 0 else self.layer.pop_right()
-                        got = len(arr)
-                        sb[: got * RECORD] = torch.from_numpy(
-                            np.frombuffer(arr.tobytes(), dtype=np.uint8).copy())
-                    assert got == n_send[d]
-                    ops.append(dist.P2POp(dist.isend, sb[: got * RECORD], self._global(peer),
-                                          group=self.group))
-                    self.migrations_out += got
-                if n_recv[d] > 0:
-                    rb = self._buffer(f"recv{d}", n_recv[d])
-                    recv_bufs[d] = rb
-                    ops.append(dist.P2POp(dist.irecv, rb[: n_recv[d] * RECORD],
-                                          self._global(peer), group=self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-            if self.on_device:
-                torch.cuda.current_stream(self.tdev).synchronize()
-        for d, rb in recv_bufs.items():
-            if self.on_device:
-                self.layer.push_device(rb.data_ptr(), n_recv[d])
-            else:
-                raw = rb[: n_recv[d] * RECORD].numpy().tobytes()
-                self.layer.push(np.frombuffer(raw, dtype=PARTICLE_DTYPE))
-        return int(table[:, 2].sum())
+            if not 0 <= peer < K:
+                continue
+            if n_send[d] > 0:
+                sb = self._buffer(f"send{d}.{parity}", n_send[d])
+                if self.on_device:
+                    got = self.layer.pop_device(side, sb.data_ptr(), n_send[d])
+                else:
+                    arr = self.layer.pop_left() if side == 0 else self.layer.pop_right()
+                    got = len(arr)
+                    sb[: got * RECORD] = torch.from_numpy(
+                        np.frombuffer(arr.tobytes(), dtype=np.uint8).copy())
+                assert got == n_send[d]
+                ops.append(dist.P2POp(dist.isend, sb[: got * RECORD], self._global(peer),
+                                      group=self.group))
+                self.migrations_out += got
+            if n_recv[d] > 0:
+                rb = self._buffer(f"recv{d}.{parity}", n_recv[d])
+                recv_bufs[d] = (rb, n_recv[d])
+                ops.append(dist.P2POp(dist.irecv, rb[: n_recv[d] * RECORD],
+                                      self._global(peer), group=self.group))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        return reqs, recv_bufs
 
-    def _global(self, group_rank: int) -> int:
-        return dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+    def _finish_exchange(self, pending):
+        """wait for the transfers and append what arrived to the bank"""
+        if pending is None:
+            return
+        reqs, recv_bufs = pending
+        for req in reqs:
+            req.wait()
+        if reqs and self.on_device:
+            torch.cuda.current_stream(self.tdev).synchronize()
+        for d, (rb, n) in recv_bufs.items():
+            if self.on_device:
+                self.layer.push_device(rb.data_ptr(), n)
+            else:
+                raw = rb[: n * RECORD].numpy().tobytes()
+                self.layer.push(np.frombuffer(raw, dtype=PARTICLE_DTYPE))
 
     def spin(self, max_cycles=10_000_000) -> dict:
         """Worker::spin: cycle until every source particle is disabled somewhere."""
         total = self.cfg.nb_particles
         births = min(self.ramp_from, self.per_cycle) if self.ramp_from else self.per_cycle
+        pending = None
         while self.cycles < max_cycles:
             t0 = time.perf_counter()
             if self.ramp_from:
@@ -185,12 +193,20 @@ class SlabWorld:
             else:
                 c = self.layer.simulate(self.per_cycle)
             t1 = time.perf_counter()
-            disabled = self._exchange(c)
+            table = self._gather_counts(c)
+            # the previous cycle's transfers ran under this cycle's tracking
+            self._finish_exchange(pending)
+            pending = self._start_exchange(table, self.cycles & 1)
+            if not self.overlap:
+                self._finish_exchange(pending)
+                pending = None
             t2 = time.perf_counter()
             self.t_simulate += t1 - t0
             self.t_exchange += t2 - t1
             self.cycles += 1
-            if disabled == total:
+            if int(table[:, 2].sum()) == total:
+                # every source particle is disabled somewhere: nothing can be in flight
+                self._finish_exchange(pending)
                 break
         else:
             raise RuntimeError("SlabWorld.spin: did not terminate")
@@ -207,7 +223,7 @@ class SlabWorld:
         slices concatenated on rank 0 (None elsewhere); float64 view of the exact tally."""
         K = self.world_size
         mine = torch.from_numpy(np.ascontiguousarray(self.layer.weights_absorbed_f64))
-        sizes = [split_cells(self.cfg.nb_cells, K, r)[1] for r in range(K)]
+        sizes = [self.cuts[r + 1] - self.cuts[r] for r in range(K)]
         m_max = max(sizes)
         pad = torch.zeros(m_max, dtype=torch.float64)
         pad[: mine.numel()] = mine

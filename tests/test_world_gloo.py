@@ -52,7 +52,7 @@ class OracleAsLayer:
         return self.o.tally_exact_f64
 
 
-def _worker(rank, K, port, n, per_cycle, q):
+def _worker(rank, K, port, n, per_cycle, overlap, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -62,7 +62,8 @@ def _worker(rank, K, port, n, per_cycle, q):
         from mc_mpi_b200 import configs
         from mc_mpi_b200.world import SlabWorld
         cfg = configs.reference_default(n)
-        w = SlabWorld(cfg, nb_particles_per_cycle=per_cycle, layer=OracleAsLayer(cfg, K, rank))
+        w = SlabWorld(cfg, nb_particles_per_cycle=per_cycle, layer=OracleAsLayer(cfg, K, rank),
+                      global_dx=False, overlap=overlap)
         s = w.spin()
         wa = w.gather_weights_absorbed()
         q.put((rank, s["cycles"], s["migrations_out"], s["nb_disabled"], s["events"],
@@ -77,8 +78,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("K,n,per_cycle", [(2, 1500, 400), (3, 900, 100_000)])
-def test_slab_world_over_gloo(K, n, per_cycle):
+@pytest.mark.parametrize("K,n,per_cycle,overlap", [(2, 1500, 400, False), (3, 900, 100_000, False),
+                                                   (3, 1200, 300, True)])
+def test_slab_world_over_gloo(K, n, per_cycle, overlap):
     sys.path.insert(0, HERE)
     from mc_mpi_b200 import configs
     from util import oracle_chain
@@ -89,14 +91,19 @@ def test_slab_world_over_gloo(K, n, per_cycle):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, K, port, n, per_cycle, q)) for r in range(K)]
+    procs = [ctx.Process(target=_worker, args=(r, K, port, n, per_cycle, overlap, q))
+             for r in range(K)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in range(K))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert [r[1] for r in res] == [cycles] * K                 # every rank left the loop together
+    assert len({r[1] for r in res}) == 1                        # every rank left the loop together
+    if not overlap:                                             # lock-step == the sync worker's cycles
+        assert res[0][1] == cycles
+    else:                                                       # transfers one cycle in flight
+        assert res[0][1] >= cycles
     assert sum(r[2] for r in res) == mig                        # migrations
     assert [r[3] for r in res] == [l.nb_disabled for l in layers]
     assert sum(r[3] for r in res) == n                          # termination criterion
