@@ -233,7 +233,8 @@ def run_gpu_arm(args):
     else:
         from mc_mpi_b200.world import SlabWorld, balanced_cuts
         sw = SlabWorld(cfg, device=local_rank, nb_particles_per_cycle=args.per_cycle,
-                       ramp_from=args.ramp_from if args.ramp_from > 0 else None)
+                       ramp_from=args.ramp_from if args.ramp_from > 0 else None,
+                       overlap=args.overlap)
         layer = sw.layer
 
         def step():
@@ -261,6 +262,12 @@ def run_gpu_arm(args):
         layer = sw.layer
     stream = torch.cuda.ExternalStream(layer.stream_ptr, device=torch.device("cuda", local_rank))
     barrier()
+    if world > 1:   # the host-side split reported below covers the timed steps only
+        sw.cycles = 0
+        sw.t_simulate = sw.t_exchange = 0.0
+        sw.t_parts = {k: 0.0 for k in sw.t_parts}
+        if os.environ.get("MCB200_TRACE_DIR"):
+            sw.trace = []
     c0 = layer.counts()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -291,6 +298,11 @@ def run_gpu_arm(args):
     value = n_hist * args.steps / (dev_ms * 1e-3)
     world_info = None
     if world > 1:
+        if sw.trace is not None:
+            with open(os.path.join(os.environ["MCB200_TRACE_DIR"], f"trace_rank{rank}.json"), "w") as f:
+                json.dump({"columns": ["cycle", "simulate_ms", "track_ms_cum", "gather_ms",
+                                       "start_ms", "finish_ms", "n_out_left", "n_out_right",
+                                       "n_bank_after", "n_unborn_after"], "rows": sw.trace}, f)
         world_info = {"cycles": sw.cycles,
                       "t_simulate_s_max": max_over_ranks(sw.t_simulate),
                       "t_exchange_s_max": max_over_ranks(sw.t_exchange),
@@ -301,6 +313,8 @@ def run_gpu_arm(args):
                       "segments_per_rank": per_rank(float(
                           sum(c1[k] - c0[k] for k in ("n_left", "n_right", "n_dead")))),
                       "cuts": sw.cuts, "balanced": bool(args.balance and args.warmup > 1),
+                      "overlap": sw.overlap,
+                      "host_split_s_per_rank": {k: per_rank(v) for k, v in sw.t_parts.items()},
                       "ramp_from": args.ramp_from,
                       "note": "host wall-clock split of SlabWorld.spin over warm-up + timed steps; "
                               "track_ms = tracking-kernel time of the timed steps"}
@@ -401,6 +415,8 @@ def main():
     ap.add_argument("--per-cycle", type=int, default=1 << 24, dest="per_cycle")
     ap.add_argument("--ramp-from", type=int, default=1 << 20, dest="ramp_from",
                     help="source histories of the first cycle (doubling up to --per-cycle); 0 = flat")
+    ap.add_argument("--overlap", action="store_true",
+                    help="keep the exchange of cycle c in flight under the tracking of cycle c+1")
     ap.add_argument("--no-balance", action="store_false", dest="balance",
                     help="keep the reference's equal-cell-count decomposition")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, dest="cpu_sample")

@@ -88,6 +88,9 @@ class SlabWorld:
         self.cycles = 0
         self.migrations_out = 0
         self.t_simulate = self.t_exchange = 0.0
+        self.trace = None   # set to [] to record one tuple per cycle (see spin)
+        self.t_parts ={"counts": 0.0, "simulate": 0.0, "gather": 0.0, "finish": 0.0, "start": 0.0,
+                        "start.pop": 0.0, "start.post": 0.0, "finish.wait": 0.0, "finish.push": 0.0}
 
     def _make_layer(self):
         cfg = self.cfg
@@ -142,7 +145,9 @@ class SlabWorld:
             if n_send[d] > 0:
                 sb = self._buffer(f"send{d}.{parity}", n_send[d])
                 if self.on_device:
+                    _t = time.perf_counter()
                     got = self.layer.pop_device(side, sb.data_ptr(), n_send[d])
+                    self.t_parts["start.pop"] += time.perf_counter() - _t
                 else:
                     arr = self.layer.pop_left() if side == 0 else self.layer.pop_right()
                     got = len(arr)
@@ -157,7 +162,9 @@ class SlabWorld:
                 recv_bufs[d] = (rb, n_recv[d])
                 ops.append(dist.P2POp(dist.irecv, rb[: n_recv[d] * RECORD],
                                       self._global(peer), group=self.group))
+        _t = time.perf_counter()
         reqs = dist.batch_isend_irecv(ops) if ops else []
+        self.t_parts["start.post"] += time.perf_counter() - _t
         return reqs, recv_bufs
 
     def _finish_exchange(self, pending):
@@ -165,16 +172,20 @@ class SlabWorld:
         if pending is None:
             return
         reqs, recv_bufs = pending
+        _t = time.perf_counter()
         for req in reqs:
             req.wait()
         if reqs and self.on_device:
             torch.cuda.current_stream(self.tdev).synchronize()
+        self.t_parts["finish.wait"] += time.perf_counter() - _t
+        _t = time.perf_counter()
         for d, (rb, n) in recv_bufs.items():
             if self.on_device:
                 self.layer.push_device(rb.data_ptr(), n)
             else:
                 raw = rb[: n * RECORD].numpy().tobytes()
                 self.layer.push(np.frombuffer(raw, dtype=PARTICLE_DTYPE))
+        self.t_parts["finish.push"] += time.perf_counter() - _t
 
     def spin(self, max_cycles=10_000_000) -> dict:
         """Worker::spin: cycle until every source particle is disabled somewhere."""
@@ -183,26 +194,40 @@ class SlabWorld:
         pending = None
         while self.cycles < max_cycles:
             t0 = time.perf_counter()
+            ta = t0
             if self.ramp_from:
                 # everything received so far + this cycle's share of the source
                 st = self.layer.counts()
                 unborn = st["n_unborn"]
                 b = min(births, max(unborn // 2, self.ramp_from)) if unborn > 0 else 0
+                ta = time.perf_counter()
                 c = self.layer.simulate(st["n_bank"] + b)
                 births = min(births * 2, self.per_cycle)
             else:
                 c = self.layer.simulate(self.per_cycle)
             t1 = time.perf_counter()
             table = self._gather_counts(c)
+            tb = time.perf_counter()
             # the previous cycle's transfers ran under this cycle's tracking
             self._finish_exchange(pending)
+            tc = time.perf_counter()
             pending = self._start_exchange(table, self.cycles & 1)
+            td = time.perf_counter()
             if not self.overlap:
                 self._finish_exchange(pending)
                 pending = None
             t2 = time.perf_counter()
             self.t_simulate += t1 - t0
             self.t_exchange += t2 - t1
+            for k, v in (("counts", ta - t0), ("simulate", t1 - ta), ("gather", tb - t1),
+                         ("finish", (tc - tb) + (t2 - td)), ("start", td - tc)):
+                self.t_parts[k] += v
+            if self.trace is not None:
+                self.trace.append((self.cycles, round((t1 - ta) * 1e3, 3), round(c["track_ms"], 3),
+                                   round((tb - t1) * 1e3, 3), round((td - tc) * 1e3, 3),
+                                   round(((tc - tb) + (t2 - td)) * 1e3, 3),
+                                   int(table[self.rank, 0]), int(table[self.rank, 1]),
+                                   c["n_bank"], c["n_unborn"]))
             self.cycles += 1
             if int(table[:, 2].sum()) == total:
                 # every source particle is disabled somewhere: nothing can be in flight
