@@ -296,6 +296,16 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         achieved_min = float(t.item())
     value = n_hist * args.steps / (dev_ms * 1e-3)
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full`
+    # capture (bytes per history x histories per launch)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "track_kernel_dram.json")) as f:
+            per_hist = float(json.load(f)["dram_bytes_per_history"])
+        traffic = per_hist * (sum_over_ranks(float(sum(c1[k] - c0[k] for k in ("n_left", "n_right", "n_dead"))))
+                              / max(sum_over_ranks(float(launches)), 1.0))
+    except Exception:
+        pass
     world_info = None
     if world > 1:
         if sw.trace is not None:
@@ -392,7 +402,7 @@ def run_gpu_arm(args):
             "events_per_s": events / (dev_ms * 1e-3),
             "wall_s": wall,
             "roofline": {"bound": "hbm", "achieved": achieved_min, "peak": peak, "unit": "GB/s",
-                         "frac": achieved_min / peak, "traffic": None,
+                         "frac": achieved_min / peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "model": f"{BYTES_PER_EVENT} B/event x events / track_kernel time "
                                   f"({launches} launches, {track_ms / max(launches, 1):.3f} ms avg"
@@ -412,7 +422,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["mcb200", "reference"], default="mcb200")
     ap.add_argument("--particles", type=int, default=None, help="histories per step (override)")
-    ap.add_argument("--per-cycle", type=int, default=1 << 24, dest="per_cycle")
+    ap.add_argument("--per-cycle", type=int, default=1 << 25, dest="per_cycle")
     ap.add_argument("--ramp-from", type=int, default=1 << 20, dest="ramp_from",
                     help="source histories of the first cycle (doubling up to --per-cycle); 0 = flat")
     ap.add_argument("--overlap", action="store_true",
