@@ -298,18 +298,29 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
       const int il = idx - lo;                                   // :129
-      const CellXs xs = SHARED ? lds_f32x2(xs_s + (unsigned)il * 8u)
+      const CellXs xs = SHARED ? lds_f32x4(xs_s + (unsigned)il * 16u)
                                : __ldg(&p.xs[il]);               // :131-133
       seed = lcg_next(seed);                                     // :136
       const float h = lcg_to_real(seed);
-      float di = MCB_MAXREAL;                                    // :137
-      if (xs.y > MCB_EPS) di = __fdiv_rn(-logf_glibc(h, tb_s), xs.y);
 
       const bool neg = mu < 0.0f;                                // :143-152
       int inew = neg ? idx - 1 : idx + 1;
       const float xe = __fmul_rn(__int2float_rn(neg ? idx : idx + 1), dx);
       float de = MCB_MAXREAL;                                    // :154-158
       if (mu < -MCB_EPS || MCB_EPS < mu) de = __fdiv_rn(__fsub_rn(xe, x), mu);
+
+      // :137 di = -logf(h)/sig_i, :160 `di < di_edge`.  The reference only uses di when the
+      // flight ends inside the cell; when it reaches the edge, di is overwritten (:170).  Since
+      // -ln h >= 1 - h, a flight is CERTAIN to reach the edge when (1 - h)/sig_i exceeds
+      // di_edge by more than all roundings involved: glibc's logf is within 1 ulp, the two
+      // float divisions / products within 2^-24 each, xs.z is 1/sig_i lowered by 2^-20, and
+      // the margin asked for here is 2^-18.  On a thin slab that is 99.9 % of the events, and
+      // they skip the logf and the divide without changing one bit of the result; the others
+      // take the exact path.  (xs.z = +inf for sig_i <= EPS; NaN / inf compare false -> exact.)
+      float di = MCB_MAXREAL;
+      const bool certain_edge =
+          __fmul_rn(__fsub_rn(1.0f, h), xs.z) > __fmul_rn(de, 1.0f + 0x1p-18f);
+      if (!certain_edge && xs.y > MCB_EPS) di = __fdiv_rn(-logf_glibc(h, tb_s), xs.y);
 
       if (di < de) {                                             // :160-166
         inew = idx;

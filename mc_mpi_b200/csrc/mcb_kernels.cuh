@@ -48,7 +48,9 @@ struct DevCounters {
 // per-cell constants of the event, precomputed once per layer from the public
 // sigs / absorption_rates vectors exactly as src/layer.cpp:131-133 does
 //   .x = sig_a = sigs*a          .y = sig_i = sigs*(float)(1.0 - a)
-typedef float2 CellXs;
+//   .z = a float just BELOW 1/sig_i (by 2^-20; +inf when sig_i <= EPS), used only by the
+//        "certain crossing" test of the event (see track_kernel); .w unused
+typedef float4 CellXs;
 
 struct TrackParams {
   // particle bank, structure of arrays of vectors: seed[] (8 B) and

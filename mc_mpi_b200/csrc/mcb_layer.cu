@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <vector>
@@ -185,7 +186,11 @@ int upload_xs(mcb200_layer *l) {
     const float interaction_rate = (float)(1.0 - (double)a);
     const float sig_a = l->sigs[(size_t)i] * a;
     const float sig_i = l->sigs[(size_t)i] * interaction_rate;
-    xs[(size_t)i] = make_float2(sig_a, sig_i);
+    // a float safely below 1/sig_i for the kernel's "certain crossing" test
+    const float inv_lb = sig_i > MCB_EPS
+                             ? (float)((1.0 / (double)sig_i) * (1.0 - 0x1p-20))
+                             : std::numeric_limits<float>::infinity();
+    xs[(size_t)i] = make_float4(sig_a, sig_i, inv_lb, 0.0f);
   }
   MCB_CUDA(cudaMemcpyAsync(l->d_xs, xs.data(), xs.size() * sizeof(mcb::CellXs),
                            cudaMemcpyHostToDevice, l->stream));
