@@ -190,6 +190,11 @@ int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host,
 /* device logf / expf as used by the tracking kernel, element-wise */
 int mcb200_test_logf(int device, const float *in_host, float *out_host, int64_t n);
 int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t n);
+/* di_edge = (x_edge - x) / mu (src/layer.cpp:154-158) as the kernel computes it: IEEE
+ * division with the reciprocal of mu hoisted out of the event loop; out = FLT_MAX where
+ * |mu| <= 1e-4 */
+int mcb200_test_edge_distance(int device, const float *a_host, const float *mu_host,
+                              float *out_host, int64_t n);
 /* the exact accumulator the tally uses: sum of n floats -> 4 digits (+ rounded double) */
 int mcb200_test_accumulate(int device, const float *in_host, int64_t n,
                            uint32_t *out4, double *out_f64);

@@ -87,6 +87,7 @@ SYMBOLS = {
     "mcb200_test_rnd_real": (C.c_int, [C.c_int, _P, _P, _I64]),
     "mcb200_test_logf": (C.c_int, [C.c_int, _P, _P, _I64]),
     "mcb200_test_expf": (C.c_int, [C.c_int, _P, _P, _I64]),
+    "mcb200_test_edge_distance": (C.c_int, [C.c_int, _P, _P, _P, _I64]),
     "mcb200_test_accumulate": (C.c_int, [C.c_int, _P, _I64, _P, C.POINTER(C.c_double)]),
     "mcb200_test_birth": (C.c_int, [C.c_int, _F, _F, _F, _I64, C.c_uint64, _P]),
 }

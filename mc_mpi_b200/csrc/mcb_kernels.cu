@@ -144,6 +144,24 @@ __device__ __forceinline__ void acc_merge(unsigned *w, int stride, const unsigne
   }
 }
 
+// a / b in round-to-nearest with the reciprocal hoisted out of the event loop.  div.rn.f32's
+// fast path is  r0 = MUFU.RCP(b); r = r0 + r0*(1 - b*r0); q0 = a*r; q = q0 + r*(a - b*q0)
+// guarded by FCHK (exponent ranges).  `b` (the direction cosine) only changes when a particle
+// scatters, so r is computed then; the per-event part is 3 FFMA.  The guard used here is
+// stricter than FCHK: |b| in (EPS, 2^60) when r is formed, |a| in [2^-100, 2^100) per event;
+// anything else takes __fdiv_rn.
+__device__ __forceinline__ float recip_for_div(float b) {
+  const float ab = fabsf(b);
+  if (!(ab > MCB_EPS && ab < 0x1p60f)) return 0.0f;  // 0 = "no fast path for this divisor"
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
+  return __fmaf_rn(r0, __fmaf_rn(-b, r0, 1.0f), r0);
+}
+__device__ __forceinline__ float div_by_recip(float a, float b, float r) {
+  const float q0 = __fmul_rn(a, r);
+  return __fmaf_rn(r, __fmaf_rn(-b, q0, a), q0);
+}
+
 struct TrackSmem {
   MathTables math;
   unsigned int n_cls[3];
@@ -197,6 +215,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
   // particle state, include/types/particle.hpp:7-18, one history per lane
   unsigned long long seed = 0;
   float x = 0.f, mu = 0.f, wmc = 0.f;
+  float rmu = 0.f;  // recip_for_div(mu), refreshed whenever mu changes
   int idx = 0;
   bool active = false;
   bool exhausted = false;  // warp-uniform: the bank range has been handed out
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
           const float4 st = __ldcs(&p.bank_st[slot]);
           x = st.x;
           mu = st.y;
+          rmu = recip_for_div(mu);
           wmc = st.z;
           idx = __float_as_int(st.w);
           active = true;
@@ -307,7 +327,12 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
       int inew = neg ? idx - 1 : idx + 1;
       const float xe = __fmul_rn(__int2float_rn(neg ? idx : idx + 1), dx);
       float de = MCB_MAXREAL;                                    // :154-158
-      if (mu < -MCB_EPS || MCB_EPS < mu) de = __fdiv_rn(__fsub_rn(xe, x), mu);
+      {
+        const float a = __fsub_rn(xe, x);
+        const unsigned ea = (__float_as_uint(a) & 0x7fffffffu) - 0x0d800000u;  // 2^-100 ..
+        if (rmu != 0.0f && ea < 0x64000000u) de = div_by_recip(a, mu, rmu);    // .. 2^100
+        else if (mu < -MCB_EPS || MCB_EPS < mu) de = __fdiv_rn(a, mu);
+      }
 
       // :137 di = -logf(h)/sig_i, :160 `di < di_edge`.  The reference only uses di when the
       // flight ends inside the cell; when it reaches the edge, di is overwritten (:170).  Since
@@ -327,6 +352,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
         x = __fadd_rn(x, __fmul_rn(di, mu));
         seed = lcg_next(seed);
         mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
+        rmu = recip_for_div(mu);
         ++n_sc;
       } else {                                                   // :167-172
         di = de;
@@ -601,6 +627,26 @@ __global__ void test_math_kernel(int which, long long n, const float *in, float 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = which == 0 ? logf_glibc(in[i], tb) : expf_glibc_nonpos(in[i], tb);
+}
+
+// the hoisted-reciprocal division exactly as the event uses it (guards and fallback included)
+__global__ void test_div_kernel(long long n, const float *a, const float *b, float *out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float r = recip_for_div(b[i]);
+    const unsigned ea = (__float_as_uint(a[i]) & 0x7fffffffu) - 0x0d800000u;
+    float q = MCB_MAXREAL;
+    if (r != 0.0f && ea < 0x64000000u) q = div_by_recip(a[i], b[i], r);
+    else if (b[i] < -MCB_EPS || MCB_EPS < b[i]) q = __fdiv_rn(a[i], b[i]);
+    out[i] = q;
+  }
+}
+
+cudaError_t launch_test_div(long long n, const float *a, const float *b, float *out,
+                            cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  test_div_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(n, a, b, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_test_math(int which, long long n, const float *in, float *out,

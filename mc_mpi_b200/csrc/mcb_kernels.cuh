@@ -121,6 +121,8 @@ cudaError_t launch_test_rnd_real(long long n, unsigned long long *seeds,
                                  float *out, cudaStream_t stream);
 cudaError_t launch_test_math(int which, long long n, const float *in, float *out,
                              cudaStream_t stream);
+cudaError_t launch_test_div(long long n, const float *a, const float *b, float *out,
+                            cudaStream_t stream);
 // exact accumulation of n floats into ONE accumulator (kAccDigits words)
 cudaError_t launch_test_accumulate(long long n, const float *in, unsigned *acc4,
                                    cudaStream_t stream);

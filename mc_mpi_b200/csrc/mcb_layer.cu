@@ -808,6 +808,27 @@ int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t 
   return test_math(1, device, in_host, out_host, n);
 }
 
+int mcb200_test_edge_distance(int device, const float *a_host, const float *mu_host,
+                              float *out_host, int64_t n) {
+  if (n < 0 || (n > 0 && (!a_host || !mu_host || !out_host)))
+    return fail(MCB200_ERR_INVALID, "test_edge_distance: bad argument");
+  if (n == 0) return MCB200_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "test_edge_distance: cudaSetDevice failed");
+  float *da = nullptr, *db = nullptr, *dout = nullptr;
+  MCB_CUDA(cudaMalloc(&da, (size_t)n * 4));
+  MCB_CUDA(cudaMalloc(&db, (size_t)n * 4));
+  MCB_CUDA(cudaMalloc(&dout, (size_t)n * 4));
+  MCB_CUDA(cudaMemcpy(da, a_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(cudaMemcpy(db, mu_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_div(n, da, db, dout, nullptr));
+  MCB_CUDA(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dout);
+  return MCB200_OK;
+}
+
 int mcb200_test_accumulate(int device, const float *in_host, int64_t n, uint32_t *out4,
                            double *out_f64) {
   if (n < 0 || (n > 0 && !in_host) || !out4)

@@ -120,3 +120,29 @@ def test_exact_accumulator_device_equals_checker(gpu, mcb_lib):
     bad = np.array([1.0, 200.0], dtype=np.float32)
     got = np.zeros(4, dtype=np.uint32)
     assert mcb_lib.mcb200_test_accumulate(gpu, bad.ctypes.data, 2, got.ctypes.data, None) == _abi.ERR_RANGE
+
+
+def test_edge_distance_division_is_ieee(gpu, mcb_lib):
+    """di_edge = (x_edge - x)/mu with the reciprocal of mu hoisted out of the event loop must be
+    the IEEE round-to-nearest quotient the reference's x86 divss gives, for every operand."""
+    rng = np.random.default_rng(21)
+    n = 4_000_000
+    mu = (rng.random(n, dtype=np.float32) * np.float32(2) - np.float32(1)).astype(np.float32)
+    a = np.concatenate([
+        (rng.random(n // 2, dtype=np.float32) * np.float32(0.01)).astype(np.float32),      # cell-sized
+        rng.integers(0, 0x7f800000, size=n // 4, dtype=np.uint32).view(np.float32),          # any exponent
+        -rng.integers(0, 0x7f800000, size=n // 4, dtype=np.uint32).view(np.float32),
+    ]).astype(np.float32)
+    # special operands: zeros, denormals, huge / tiny mu, +-EPS
+    sa = np.array([0.0, -0.0, 1e-45, 1e-38, 1.0, 3.4e38, 1e-30, 0.001, 0.001, 0.001, 0.001, 0.5],
+                  dtype=np.float32)
+    sm = np.array([0.5, 0.5, 0.5, 0.5, 1e-4, 0.5, 1.0, 1e-4, 1.0001e-4, -1.0001e-4, 0.0, 3e30],
+                  dtype=np.float32)
+    a, mu = np.concatenate([a, sa]), np.concatenate([mu, sm])
+    out = np.empty_like(a)
+    _abi.check(mcb_lib.mcb200_test_edge_distance(gpu, a.ctypes.data, mu.ctypes.data,
+                                                 out.ctypes.data, a.size))
+    eps = np.float32(1e-4)
+    with np.errstate(all="ignore"):
+        want = np.where((mu < -eps) | (eps < mu), a / mu, np.float32(3.402823466e+38)).astype(np.float32)
+    assert np.array_equal(bits(out), bits(want))
