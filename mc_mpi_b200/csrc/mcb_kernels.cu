@@ -73,28 +73,79 @@ __device__ __noinline__ void acc_ripple(unsigned *w, int stride, int j) {
     if (atomicAdd(&w[j * stride], 1u) != 0xffffffffu) break;
 }
 
-// The hot deposit: v positive, normal, in [2^-97, 2^7) -- every per-event dw of a real
-// run.  The biased exponent with the sign bit on top is range-checked with ONE unsigned
-// compare; then 1 ATOMS.ADD when the significand sits inside a digit, 2 when it straddles.
-__device__ __forceinline__ void acc_add(unsigned *w, int stride, float v, unsigned *range_flag) {
+// ---- the GLOBAL accumulator: the same 128-bit number as two 64-bit digits ---------------
+// In global memory the accumulator of cell c is g[c] (bits 0..63) and g[ncell + c] (bits
+// 64..127): sm_100a has native 64-bit global atomics, and a weight-sized deposit (>= 2^-56)
+// lands entirely in the upper digit, so the common case is ONE fire-and-forget RED.E.ADD.64
+// with no return value to wait for.  Used per event when the CTA-private copy does not fit
+// shared memory (tally_mode 2), and once per CTA by the flush of the private copies.
+
+// exact signed add of |v| = mag * 2^-120 (mag < 2^128 given as two 64-bit halves)
+__device__ __forceinline__ void gacc_add128(unsigned long long *g, int ncell,
+                                            unsigned long long lo, unsigned long long hi,
+                                            bool negative) {
+  if (!negative) {
+    if (lo) {
+      const unsigned long long old = atomicAdd(&g[0], lo);
+      hi += old > ~lo ? 1ull : 0ull;
+    }
+    if (hi) atomicAdd(&g[ncell], hi);
+  } else {  // subtract: add the two's complement
+    const unsigned long long nlo = ~lo + 1ull;
+    unsigned long long nhi = ~hi + (lo == 0ull ? 1ull : 0ull);
+    if (nlo) {
+      const unsigned long long old = atomicAdd(&g[0], nlo);
+      nhi += old > ~nlo ? 1ull : 0ull;
+    }
+    if (nhi) atomicAdd(&g[ncell], nhi);
+  }
+}
+
+__device__ __noinline__ void gacc_add_slow(unsigned long long *g, int ncell, float v,
+                                           unsigned *range_flag) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned e = (b >> 23) & 0xffu;
+  unsigned mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
+  int pos = (int)(e ? e : 1u) - (150 + kAccLsbLog2);
+  if (pos < 0) {
+    mant = pos > -24 ? mant >> (-pos) : 0u;
+    pos = 0;
+  }
+  if (mant == 0u) return;
+  if (pos > 32 * kAccDigits - 25) {
+    atomicExch(range_flag, 1u);
+    return;
+  }
+  unsigned long long lo, hi;
+  if (pos >= 64) {
+    lo = 0ull;
+    hi = (unsigned long long)mant << (pos - 64);
+  } else {
+    lo = (unsigned long long)mant << pos;
+    hi = pos > 40 ? (unsigned long long)mant >> (64 - pos) : 0ull;
+  }
+  gacc_add128(g, ncell, lo, hi, (int)b < 0);
+}
+
+// the hot global deposit: v positive, normal, in [2^-97, 2^7)
+__device__ __forceinline__ void gacc_add(unsigned long long *g, int ncell, float v,
+                                         unsigned *range_flag) {
   const unsigned b = __float_as_uint(v);
   const unsigned pos = (b >> 23) - (unsigned)(150 + kAccLsbLog2);  // exponent (and sign) - 30
-  if (pos <= (unsigned)(32 * kAccDigits - 25)) {
-    const unsigned mant = (b & 0x7fffffu) | 0x800000u;
-    const int j = (int)(pos >> 5);
-    const unsigned o = pos & 31u;
-    const unsigned lo = mant << o;
-    const unsigned hi = __funnelshift_l(mant, 0u, o);  // bits pushed into the next digit
-    unsigned *d = &w[j * stride];
-    const unsigned old = atomicAdd(d, lo);
-    const unsigned c = hi + (old > ~lo ? 1u : 0u);
-    if (c != 0u && j < kAccDigits - 1) {
-      const unsigned old2 = atomicAdd(d + stride, c);
-      if (old2 > ~c) acc_ripple(w, stride, j + 2);
-    }
+  if (pos - 64u <= (unsigned)(32 * kAccDigits - 25 - 64)) {
+    // [2^-56, 2^7): entirely inside the upper digit -> one RED, nothing to wait for
+    const unsigned long long mant = (unsigned long long)((b & 0x7fffffu) | 0x800000u);
+    atomicAdd(&g[ncell], mant << (pos - 64u));
   } else {
-    acc_add_slow(w, stride, v, range_flag);
+    gacc_add_slow(g, ncell, v, range_flag);
   }
+}
+
+// add a CTA-private accumulator (four 32-bit digits) into the global one
+__device__ __forceinline__ void gacc_merge(unsigned long long *g, int ncell,
+                                           const unsigned d[kAccDigits]) {
+  gacc_add128(g, ncell, (unsigned long long)d[0] | ((unsigned long long)d[1] << 32),
+              (unsigned long long)d[2] | ((unsigned long long)d[3] << 32), false);
 }
 
 // The same deposit into a CTA-private accumulator in SHARED memory, addressed by its
@@ -122,25 +173,6 @@ __device__ __forceinline__ void acc_add_smem(unsigned w, unsigned stride, float 
   } else {
     acc_add_slow(static_cast<unsigned *>(__cvta_shared_to_generic(w)), (int)(stride >> 2), v,
                  range_flag);
-  }
-}
-
-// add a whole accumulator (digits d[0..3] of one cell) into another one
-__device__ __forceinline__ void acc_merge(unsigned *w, int stride, const unsigned d[kAccDigits]) {
-  unsigned c = 0u;
-#pragma unroll
-  for (int j = 0; j < kAccDigits; ++j) {
-    // digit + incoming carry, as up to two adds so that neither can exceed 32 bits
-    unsigned carry_out = 0u;
-    if (d[j]) {
-      const unsigned old = atomicAdd(&w[j * stride], d[j]);
-      carry_out += old > ~d[j] ? 1u : 0u;
-    }
-    if (c) {
-      const unsigned old = atomicAdd(&w[j * stride], c);
-      carry_out += old > ~c ? 1u : 0u;
-    }
-    c = carry_out;
   }
 }
 
@@ -187,7 +219,8 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
   const int ncell = p.m + kAccExtra;
   // CTA-private copy of the tally (digit-major) when it fits in shared memory,
   // else the L2-resident global one
-  unsigned *acc = SHARED ? reinterpret_cast<unsigned *>(s_xs + p.m) : p.acc;
+  unsigned *acc = reinterpret_cast<unsigned *>(s_xs + p.m);   // only touched when SHARED
+  unsigned long long *gacc = reinterpret_cast<unsigned long long *>(p.acc);
 
   load_math_tables(&sm->math);
   if (threadIdx.x < 3) sm->n_cls[threadIdx.x] = 0u;
@@ -240,7 +273,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
       if (fin) {
         if (SHARED) acc_add_smem(acc_s + (unsigned)(p.m + cls) * 4u, acc_stride, wmc,
                                  &p.ctr->acc_range);
-        else acc_add(&p.acc[p.m + cls], ncell, wmc, &p.ctr->acc_range);
+        else gacc_add(&gacc[p.m + cls], ncell, wmc, &p.ctr->acc_range);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -363,7 +396,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
       wmc = __fsub_rn(wmc, dw);                                  // :178
       // :179, exactly
       if (SHARED) acc_add_smem(acc_s + (unsigned)il * 4u, acc_stride, dw, &p.ctr->acc_range);
-      else acc_add(&p.acc[il], ncell, dw, &p.ctr->acc_range);
+      else gacc_add(&gacc[il], ncell, dw, &p.ctr->acc_range);
       idx = inew;                                                // :181
       ++n_ev;
     }
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
         d[j] = acc[j * ncell + c];
         any |= d[j];
       }
-      if (any) acc_merge(&p.acc[c], ncell, d);
+      if (any) gacc_merge(&gacc[c], ncell, d);
     }
   }
   if (threadIdx.x < 3) {
@@ -670,7 +703,7 @@ __global__ void test_accumulate_kernel(long long n, const float *in, unsigned *a
   if (threadIdx.x == 0) {
     unsigned d[kAccDigits];
     for (int j = 0; j < kAccDigits; ++j) d[j] = s_acc[j];
-    acc_merge(acc4, 1, d);
+    gacc_merge(reinterpret_cast<unsigned long long *>(acc4), 1, d);
   }
 }
 

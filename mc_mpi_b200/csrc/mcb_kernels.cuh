@@ -67,7 +67,8 @@ struct TrackParams {
   float dx;
   float minw;            // particle_min_weight
   // outputs
-  unsigned *acc;         // [kAccDigits][m + kAccExtra] digits, digit-major
+  unsigned *acc;         // the global tally: u64[2][m + kAccExtra] (low halves, then high
+                         // halves of the 128-bit accumulators), see gacc_add
   unsigned long long *out_rec[2];  // scratch outbox per side, 24-byte records (3 words each)
   unsigned *stripe_n;    // [2][kStripes + 1] fills; entry kStripes = the overflow segment
   int stripe_cap;        // records per stripe

@@ -6,8 +6,9 @@
 //   bank      seed[cap] (u64) + st[cap] (float4 {x, mu, wmc, bits(index)})
 //   outboxes  contiguous 24-byte wire records per side (packed from the tracking kernel's
 //             per-CTA stripes by gather_stripes after every launch)
-//   tally     u32[4][m+3] exact long accumulator (mcb_kernels.cuh)
-//   xs        float2[m] {sig_a, sig_i}
+//   tally     u64[2][m+3] exact 128-bit long accumulators (mcb_kernels.cuh): low halves,
+//             then high halves; the CTA-private copies in shared memory use 32-bit digits
+//   xs        float4[m] {sig_a, sig_i, ~1/sig_i, -}
 //
 // Nothing here computes physics on the CPU: there is no fallback path.
 #include <cmath>
@@ -95,10 +96,10 @@ struct mcb200_layer {
   long long scratch_cap[2] = {0, 0};
   unsigned *d_stripe_n = nullptr;                         // [2][kStripes + 1]
   mcb::CellXs *d_xs = nullptr;
-  unsigned *d_acc = nullptr;          // [kAccDigits][m + kAccExtra]
+  unsigned *d_acc = nullptr;          // u64[2][m + kAccExtra], see mcb_kernels.cu gacc_add
   mcb::DevCounters *d_ctr = nullptr;
   mcb::DevCounters *h_ctr = nullptr;  // pinned
-  unsigned *h_cls = nullptr;          // pinned: digits of the 3 class accumulators
+  unsigned long long *h_cls = nullptr;  // pinned: [2][3] halves of the 3 class accumulators
   void *d_stage = nullptr;            // AoS staging for push / pop
   long long stage_cap = 0;            // in particles
   bool xs_dirty = true;
@@ -208,9 +209,12 @@ int fetch_tally(mcb200_layer *l, std::vector<unsigned> *out) {
   MCB_CUDA(cudaStreamSynchronize(l->stream));
   out->resize((size_t)l->m * mcb::kAccDigits);
   const size_t nc = (size_t)l->ncell();
+  // device layout: 64-bit halves [2][ncell]; 32-bit digit j of cell c is word (j & 1) of
+  // half j / 2 (little endian)
   for (int c = 0; c < l->m; ++c)
     for (int j = 0; j < mcb::kAccDigits; ++j)
-      (*out)[(size_t)c * mcb::kAccDigits + j] = raw[(size_t)j * nc + (size_t)c];
+      (*out)[(size_t)c * mcb::kAccDigits + j] =
+          raw[(size_t)(j / 2) * 2 * nc + 2 * (size_t)c + (size_t)(j & 1)];
   return MCB200_OK;
 }
 
@@ -297,9 +301,10 @@ int track(mcb200_layer *l, long long take) {
   MCB_CUDA(cudaMemcpyAsync(l->h_ctr, l->d_ctr, sizeof(mcb::DevCounters), cudaMemcpyDeviceToHost,
                            l->stream));
   // digits of the three class accumulators (weight carried left / right / by the dead)
-  MCB_CUDA(cudaMemcpy2DAsync(l->h_cls, mcb::kAccExtra * sizeof(unsigned), l->d_acc + l->m,
-                             (size_t)l->ncell() * sizeof(unsigned),
-                             mcb::kAccExtra * sizeof(unsigned), mcb::kAccDigits,
+  MCB_CUDA(cudaMemcpy2DAsync(l->h_cls, mcb::kAccExtra * sizeof(unsigned long long),
+                             reinterpret_cast<unsigned long long *>(l->d_acc) + l->m,
+                             (size_t)l->ncell() * sizeof(unsigned long long),
+                             mcb::kAccExtra * sizeof(unsigned long long), 2,
                              cudaMemcpyDeviceToHost, l->stream));
   MCB_CUDA(cudaStreamSynchronize(l->stream));
   float ms = 0.f;
@@ -318,7 +323,8 @@ int track(mcb200_layer *l, long long take) {
   for (int k = 0; k < 3; ++k) {
     l->n_cls[k] += (long long)c.n_cls[k];
     unsigned d[mcb::kAccDigits];
-    for (int j = 0; j < mcb::kAccDigits; ++j) d[j] = l->h_cls[j * mcb::kAccExtra + k];
+    for (int j = 0; j < mcb::kAccDigits; ++j)
+      d[j] = (unsigned)(l->h_cls[(j / 2) * mcb::kAccExtra + k] >> (32 * (j & 1)));
     l->w_cls[k] = acc_to_double(d);  // the device accumulators are cumulative
   }
   l->n_out[0] += (long long)c.out_total[0];
@@ -478,7 +484,7 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   cuda_ok(cudaMalloc(&l->d_stripe_n, 2 * (mcb::kStripes + 1) * sizeof(unsigned)),
           "cudaMalloc stripe fills");
   cuda_ok(cudaMallocHost(&l->h_ctr, sizeof(mcb::DevCounters)), "cudaMallocHost counters");
-  cuda_ok(cudaMallocHost(&l->h_cls, mcb::kAccDigits * mcb::kAccExtra * sizeof(unsigned)),
+  cuda_ok(cudaMallocHost(&l->h_cls, 2 * mcb::kAccExtra * sizeof(unsigned long long)),
           "cudaMallocHost class weights");
   if (rc == MCB200_OK)
     cuda_ok(cudaMemsetAsync(l->d_acc, 0, l->acc_words() * sizeof(unsigned), l->stream),
