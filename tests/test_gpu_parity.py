@@ -59,7 +59,7 @@ CASES = {
     # BASELINE config 5 at full width: 1e6 heterogeneous cells (the tally no longer fits shared
     # memory -> global accumulator path); ~5.8e5 events per history, so few histories
     "hetero_1e6": (configs.heterogeneous(1_000_000, 48), 1, 0),
-    "hetero_20000_K3_r1": (configs.heterogeneous(20_000, 300), 3, 1),
+    "hetero_20000_K3_r2": (configs.heterogeneous(20_000, 300), 3, 2),
 }
 
 
