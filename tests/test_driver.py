@@ -1,0 +1,78 @@
+"""The config.yaml driver (mc_mpi_b200/main.py), SURVEY 8(f)-1: same keys, same one-line
+output, same out/ files as `mpirun -n K ./main config.yaml sync` (src/main.cpp, src/worker.cpp)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CONFIG = os.path.join(HERE, "golden", "config.yaml")   # the reference's own config.yaml
+
+
+def test_load_config_reads_the_reference_keys():
+    from mc_mpi_b200.main import load_config, slab_config
+    opt = load_config(CONFIG)
+    # config.yaml:1-10
+    assert opt["nb_cells"] == 1000 and opt["nb_particles"] == 100000
+    assert opt["nb_particles_per_cycle"] == 500 and opt["nthread"] == 1
+    assert opt["x_min"] == 0.0 and opt["x_max"] == 1.0
+    assert np.float32(opt["x_ini"]) == np.float32(np.sqrt(np.float32(2.0)) / np.float32(2.0))
+    assert np.float32(opt["particle_min_weight"]) == np.float32(9.99999996e-13)
+    cfg = slab_config(opt)
+    assert cfg.sigs is None and cfg.absorption_rates is None and cfg.nb_cells == 1000
+
+
+def test_malformed_config_is_fatal_like_the_reference(tmp_path):
+    from mc_mpi_b200.main import load_config
+    p = tmp_path / "bad.yaml"
+    p.write_text("nb_cells 1000\n")
+    with pytest.raises(SystemExit):
+        load_config(str(p))          # "Yaml File ... was not correctly formatted." + exit(1)
+    with pytest.raises(SystemExit):
+        load_config(str(tmp_path / "missing.yaml"))
+
+
+def test_dump_formats(tmp_path):
+    from mc_mpi_b200.main import dump_config, dump_weights_absorbed, load_config
+    opt = load_config(CONFIG)
+    dump_config(str(tmp_path / "config.yaml"), opt, 5)
+    txt = (tmp_path / "config.yaml").read_text()
+    # YamlDumper formats (src/yaml_dumper.cpp:13-24): %d, %.18e
+    assert "# Read from config\nnb_cells: 1000\nx_min: 0.000000000000000000e+00\n" in txt
+    assert "x_ini: 7.071067690849304199e-01\n" in txt and "world_size: 5\n" in txt
+    again = load_config(str(tmp_path / "config.yaml")) if False else None  # comments are not keys
+    w = np.linspace(1e-4, 2e-4, 10)
+    dump_weights_absorbed(str(tmp_path / "weights.csv"), w, [0, 4, 10], np.float32(0.1))
+    rows = (tmp_path / "weights.csv").read_text().splitlines()
+    assert rows[0] == "proc, x, weight" and len(rows) == 11
+    assert rows[1].startswith("0, ") and rows[5].startswith("1, ")     # displs switch at i == 4
+    assert re.fullmatch(r"\d+, \d\.\d{18}e[+-]\d\d, \d\.\d{18}e[+-]\d\d", rows[3])
+
+
+@pytest.mark.gpu
+def test_driver_end_to_end(gpu, tmp_path):
+    """`python -m mc_mpi_b200.main config.yaml`: one wall-time line; out/weights.csv equals the
+    oracle's tally (float view) for the reference's default workload."""
+    sys.path.insert(0, HERE)
+    from mc_mpi_b200 import configs
+    from util import make_oracle
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    res = subprocess.run([sys.executable, "-m", "mc_mpi_b200.main", CONFIG], cwd=tmp_path, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = res.stdout.strip().splitlines()
+    assert len(lines) == 1 and float(lines[0]) > 0            # main.cpp:91
+    for f in ("out/config.yaml", "out/weights.csv", "WA.out"):
+        assert (tmp_path / f).is_file()
+    got = np.loadtxt(tmp_path / "out" / "weights.csv", delimiter=",", skiprows=1)
+    assert got.shape == (1000, 3) and np.all(got[:, 0] == 0)
+    o = make_oracle(configs.reference_default(100_000))
+    o.simulate(-1, nthread=os.cpu_count() or 1)
+    dx = np.float32(o.dx)
+    want = (o.tally_exact_f64.astype(np.float32) / dx).astype(np.float64)
+    assert np.array_equal(got[:, 2], want)
+    assert np.allclose(got[:, 1], float(dx) * (np.arange(1000) + 0.5), rtol=0, atol=1e-15)
