@@ -24,13 +24,14 @@ namespace mcb {
 
 // ---------------------------------------------------------------- helpers --
 
-// Exact deposit of one float into a 128-bit accumulator (see mcb_kernels.cuh):
-// the 24-bit significand goes to bit position (exponent - 30) of a little-endian
-// number held in four 32-bit digits `w[0], w[stride], w[2*stride], w[3*stride]`.
-// Common case: one native 32-bit atomic add (ATOMS.ADD / ATOMG.ADD) when the
-// significand sits inside one digit, two when it straddles; carries ripple by
-// further adds only when a digit wraps.  The final digits do not depend on the
-// interleaving: every step is an exact add modulo 2^128.
+// ---- the CTA-PRIVATE accumulator: four 32-bit digits in shared memory ---------------------
+// Exact deposit of one float into a 128-bit accumulator (see mcb_kernels.cuh): the 24-bit
+// significand goes to bit position (exponent - 30) of a little-endian number held in four
+// 32-bit digits `w[0], w[stride], w[2*stride], w[3*stride]`.  Common case (acc_add_smem
+// below): one native ATOMS.ADD when the significand sits inside one digit, two when it
+// straddles; carries ripple by further adds only when a digit wraps.  The final digits do
+// not depend on the interleaving: every step is an exact add modulo 2^128.
+
 // general case: zeros, deposits below 2^-97, negative deposits, out-of-range values
 __device__ __noinline__ void acc_add_slow(unsigned *w, int stride, float v, unsigned *range_flag) {
   const unsigned b = __float_as_uint(v);
