@@ -234,7 +234,7 @@ def run_gpu_arm(args):
         from mc_mpi_b200.world import SlabWorld, balanced_cuts
         sw = SlabWorld(cfg, device=local_rank, nb_particles_per_cycle=args.per_cycle,
                        ramp_from=args.ramp_from if args.ramp_from > 0 else None,
-                       overlap=args.overlap)
+                       overlap=args.overlap, transport=args.transport)
         layer = sw.layer
 
         def step():
@@ -398,7 +398,10 @@ def run_gpu_arm(args):
                        "parallelism": "1 GPU" if world == 1 else
                                       f"domain decomposition, {world} sub-slabs "
                                       f"({'cuts balanced on measured tracking time' if args.balance and args.warmup > 1 else 'equal cell counts'}), "
-                                      f"<= {args.per_cycle} source histories per cycle"},
+                                      f"<= {args.per_cycle} source histories per cycle, escapees "
+                                      + ("stored by the tracking kernel into the neighbour GPU's "
+                                         "inbox over NVLink (CUDA IPC)" if args.transport == "p2p"
+                                         else "shipped with ncclSend/Recv")},
             "events_per_s": events / (dev_ms * 1e-3),
             "wall_s": wall,
             "roofline": {"bound": "hbm", "achieved": achieved_min, "peak": peak, "unit": "GB/s",
@@ -425,6 +428,9 @@ def main():
     ap.add_argument("--per-cycle", type=int, default=1 << 25, dest="per_cycle")
     ap.add_argument("--ramp-from", type=int, default=1 << 20, dest="ramp_from",
                     help="source histories of the first cycle (doubling up to --per-cycle); 0 = flat")
+    ap.add_argument("--transport", choices=["nccl", "p2p"], default="nccl",
+                    help="N > 1: nccl = outbox -> ncclSend/Recv -> bank; p2p = the tracking kernel "
+                         "stores escapees straight into the neighbour GPU's inbox over NVLink")
     ap.add_argument("--overlap", action="store_true",
                     help="keep the exchange of cycle c in flight under the tracking of cycle c+1")
     ap.add_argument("--no-balance", action="store_false", dest="balance",

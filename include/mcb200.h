@@ -153,6 +153,46 @@ int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap,
 int mcb200_layer_outbox_device(mcb200_layer *l, int32_t side, void **dev_aos_out,
                                int64_t *n_out);
 int mcb200_layer_outbox_clear(mcb200_layer *l, int32_t side);
+/* ---- direct peer exchange over NVLink ------------------------------------ */
+/* The MPI workers move escapees with Sendrecv / Isend / MPI_Put
+ * (src/worker_sync.cpp:47-108, src/async_comm.cpp, src/rma_comm.cpp:133-186).  Here a layer
+ * can own an INBOX that its neighbours' tracking kernels store into directly (peer-mapped
+ * device memory: CUDA IPC between processes, a plain pointer inside one process): the escapee
+ * stores of the kernel are the communication, like RmaComm's MPI_Put into the neighbour's
+ * window.  The inbox is double-buffered by a parity bit so that cycle c+1 can be written
+ * while cycle c is being ingested.  Protocol per cycle, on every rank:
+ *   set_exchange_parity(c & 1); simulate(..);  <barrier / all-gather across ranks>;
+ *   ingest_inbox(from left, c & 1); ingest_inbox(from right, c & 1)                          */
+#define MCB200_IPC_HANDLE_BYTES 64
+typedef struct mcb200_inbox_geom {
+  int32_t nstripes;     /* stripes per slot = max CTAs of a sender's launch */
+  int32_t stripe_cap;   /* records per stripe */
+  int64_t ovf_cap;      /* records of the overflow segment */
+  int64_t max_take;     /* max particles a sender may track per launch */
+  int64_t slot_bytes;   /* bytes of one (side, parity) slot; 4 slots in the block */
+  int64_t fills_offset; /* byte offset of the fill counters inside a slot */
+} mcb200_inbox_geom;
+/* allocate this layer's inbox for senders that track at most `max_take` particles per
+ * launch; returns the IPC handle other PROCESSES open and the geometry they need */
+int mcb200_layer_inbox_create(mcb200_layer *l, int64_t max_take,
+                              uint8_t handle_out[MCB200_IPC_HANDLE_BYTES],
+                              mcb200_inbox_geom *geom_out);
+/* route this layer's escapees on `side` (0 left, 1 right) into a neighbour's inbox:
+ * _peer: the neighbour lives in another process (handle + geometry from its inbox_create);
+ * _local: the neighbour is `other`, in this process (any device with peer access)        */
+int mcb200_layer_connect_peer(mcb200_layer *l, int32_t side,
+                              const uint8_t handle[MCB200_IPC_HANDLE_BYTES],
+                              const mcb200_inbox_geom *geom);
+int mcb200_layer_connect_local(mcb200_layer *l, int32_t side, mcb200_layer *other);
+/* unmap the neighbours' inboxes (before THEY are destroyed; escapees go to the local
+ * outboxes again) */
+int mcb200_layer_disconnect_peers(mcb200_layer *l);
+int mcb200_layer_set_exchange_parity(mcb200_layer *l, int32_t parity);
+/* append what the neighbour on `from_side` stored in this layer's inbox (given parity) to
+ * the bank and reset that slot; *n_out = particles received */
+int mcb200_layer_ingest_inbox(mcb200_layer *l, int32_t from_side, int32_t parity,
+                              int64_t *n_out);
+
 /* weights_absorbed (layer.hpp:92), m entries.  The device keeps every cell as
  * an EXACT 128-bit fixed-point sum of the per-event float deposits (order-,
  * launch- and GPU-count-independent).  _exact returns it: four little-endian

@@ -55,6 +55,16 @@ class Counts(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+IPC_HANDLE_BYTES = 64
+
+
+class InboxGeom(C.Structure):
+    _fields_ = [
+        ("nstripes", C.c_int32), ("stripe_cap", C.c_int32), ("ovf_cap", C.c_int64),
+        ("max_take", C.c_int64), ("slot_bytes", C.c_int64), ("fills_offset", C.c_int64),
+    ]
+
+
 # every symbol include/mcb200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -75,6 +85,12 @@ SYMBOLS = {
     "mcb200_layer_pop_right_device": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
     "mcb200_layer_outbox_device": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_I64)]),
     "mcb200_layer_outbox_clear": (C.c_int, [_P, _I32]),
+    "mcb200_layer_inbox_create": (C.c_int, [_P, _I64, _P, _P]),
+    "mcb200_layer_connect_peer": (C.c_int, [_P, _I32, _P, _P]),
+    "mcb200_layer_connect_local": (C.c_int, [_P, _I32, _P]),
+    "mcb200_layer_disconnect_peers": (C.c_int, [_P]),
+    "mcb200_layer_set_exchange_parity": (C.c_int, [_P, _I32]),
+    "mcb200_layer_ingest_inbox": (C.c_int, [_P, _I32, _I32, C.POINTER(_I64)]),
     "mcb200_layer_weights_absorbed": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_f64": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_exact": (C.c_int, [_P, _P, C.POINTER(_I32)]),

@@ -293,14 +293,15 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
           if (mine) {
             const unsigned my = base + (unsigned)__popc(cm & lt_mask);
             long long slot = -1;
-            if (my < (unsigned)p.stripe_cap) {
-              slot = (long long)blockIdx.x * p.stripe_cap + my;
+            if (my < (unsigned)p.stripe_cap[c]) {
+              slot = (long long)blockIdx.x * p.stripe_cap[c] + my;
             } else {  // stripe full (unbalanced CTAs): the common overflow segment
-              const unsigned o = atomicAdd(&p.stripe_n[c * (kStripes + 1) + kStripes], 1u);
-              if ((long long)o < p.ovf_cap) slot = p.ovf_base + o;
+              const unsigned o = atomicAdd(&p.fills[c][p.ovf_slot[c]], 1u);
+              if ((long long)o < p.ovf_cap[c]) slot = p.ovf_base[c] + o;
               else atomicExch(&p.ctr->overflow, 1u);
             }
             if (slot >= 0) {
+              // with a connected peer this is a store into the neighbour GPU's memory
               unsigned long long *rec = p.out_rec[c] + 3 * slot;
               rec[0] = seed;
               rec[1] = (unsigned long long)__float_as_uint(x) |
@@ -431,10 +432,10 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
     const int c = threadIdx.x;
     if (sm->n_cls[c]) atomicAdd(&p.ctr->n_cls[c], (unsigned long long)sm->n_cls[c]);
   }
-  if (threadIdx.x < 2) {
-    const unsigned n = sm->out_n[threadIdx.x];
-    p.stripe_n[threadIdx.x * (kStripes + 1) + blockIdx.x] =
-        n < (unsigned)p.stripe_cap ? n : (unsigned)p.stripe_cap;
+  if (threadIdx.x < 2 && p.write_side[threadIdx.x]) {
+    const int c = threadIdx.x;
+    const unsigned n = sm->out_n[c];
+    p.fills[c][blockIdx.x] = n < (unsigned)p.stripe_cap[c] ? n : (unsigned)p.stripe_cap[c];
   }
 }
 
@@ -508,34 +509,59 @@ cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStrea
 // CTA s packs segment s (stripe s, or the overflow segment for s == nstripes) behind the
 // segments before it: an exclusive prefix over <= kStripes + 1 fills (block reduction),
 // then a linear, coalesced copy of 8-byte words.
+// `fills[s]` = records in stripe s, `fills[nstripes]` = records in the overflow segment.
+// TO_BANK = false: copy the wire records as they are (outbox); true: unpack them into the
+// bank layout (inbox of a direct peer exchange).
+template <bool TO_BANK>
 __global__ void __launch_bounds__(256) gather_stripes_kernel(
-    const unsigned long long *__restrict__ scratch, const unsigned *__restrict__ stripe_n,
-    int nstripes, int stripe_cap, long long ovf_base, unsigned long long *__restrict__ settled,
-    long long settled_n, unsigned long long *out_total) {
+    const unsigned long long *__restrict__ scratch, const unsigned *__restrict__ fills,
+    int nstripes, int stripe_cap, long long ovf_base, unsigned long long *__restrict__ dst_rec,
+    float4 *__restrict__ dst_st, long long dst_n, unsigned long long *out_total) {
   __shared__ unsigned long long s_part[8];
   const int seg = blockIdx.x;
   unsigned long long before = 0ull;
-  for (int t = threadIdx.x; t < seg; t += blockDim.x) before += stripe_n[t];
+  for (int t = threadIdx.x; t < seg; t += blockDim.x) before += fills[t];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(MCB_FULL, before, o);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = before;
   __syncthreads();
   before = 0ull;
   for (int w = 0; w < (int)(blockDim.x >> 5); ++w) before += s_part[w];
-  const unsigned n = stripe_n[seg == nstripes ? kStripes : seg];
+  const unsigned n = fills[seg];
   const long long src = seg == nstripes ? ovf_base : (long long)seg * stripe_cap;
   const unsigned long long *from = scratch + 3 * src;
-  unsigned long long *to = settled + 3 * (settled_n + (long long)before);
-  for (unsigned i = threadIdx.x; i < 3u * n; i += blockDim.x) to[i] = from[i];
+  if (!TO_BANK) {
+    unsigned long long *to = dst_rec + 3 * (dst_n + (long long)before);
+    for (unsigned i = threadIdx.x; i < 3u * n; i += blockDim.x) to[i] = from[i];
+  } else {
+    const long long base = dst_n + (long long)before;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long a = from[3 * i], b = from[3 * i + 1], c = from[3 * i + 2];
+      dst_rec[base + i] = a;  // the bank's seed array
+      dst_st[base + i] =
+          make_float4(__uint_as_float((unsigned)b), __uint_as_float((unsigned)(b >> 32)),
+                      __uint_as_float((unsigned)c), __uint_as_float((unsigned)(c >> 32)));
+    }
+  }
   if (seg == nstripes && threadIdx.x == 0) *out_total = before + n;
 }
 
-cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsigned *stripe_n,
+cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsigned *fills,
                                   int nstripes, int stripe_cap, long long ovf_base,
                                   unsigned long long *settled, long long settled_n,
                                   unsigned long long *out_total, cudaStream_t stream) {
-  gather_stripes_kernel<<<nstripes + 1, 256, 0, stream>>>(scratch, stripe_n, nstripes, stripe_cap,
-                                                          ovf_base, settled, settled_n, out_total);
+  gather_stripes_kernel<false><<<nstripes + 1, 256, 0, stream>>>(
+      scratch, fills, nstripes, stripe_cap, ovf_base, settled, nullptr, settled_n, out_total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_stripes_to_bank(const unsigned long long *scratch,
+                                          const unsigned *fills, int nstripes, int stripe_cap,
+                                          long long ovf_base, unsigned long long *bank_seed,
+                                          float4 *bank_st, long long bank_n,
+                                          unsigned long long *out_total, cudaStream_t stream) {
+  gather_stripes_kernel<true><<<nstripes + 1, 256, 0, stream>>>(
+      scratch, fills, nstripes, stripe_cap, ovf_base, bank_seed, bank_st, bank_n, out_total);
   return cudaGetLastError();
 }
 

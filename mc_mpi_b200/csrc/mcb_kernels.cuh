@@ -69,11 +69,16 @@ struct TrackParams {
   // outputs
   unsigned *acc;         // the global tally: u64[2][m + kAccExtra] (low halves, then high
                          // halves of the 128-bit accumulators), see gacc_add
-  unsigned long long *out_rec[2];  // scratch outbox per side, 24-byte records (3 words each)
-  unsigned *stripe_n;    // [2][kStripes + 1] fills; entry kStripes = the overflow segment
-  int stripe_cap;        // records per stripe
-  long long ovf_base;    // first record of the overflow segment (= grid * stripe_cap)
-  long long ovf_cap;     // its capacity
+  // striped outbox per side (24-byte records, 3 words each).  The memory is either this
+  // layer's own scratch (packed afterwards by gather_stripes) or -- direct peer exchange --
+  // the NEIGHBOUR GPU's inbox, mapped over NVLink: then the escapee stores of the tracking
+  // kernel ARE the communication.
+  unsigned long long *out_rec[2];
+  unsigned *fills[2];    // per side: fill of stripe b at [b]; overflow segment's at [ovf_slot]
+  int ovf_slot[2];       // index of the overflow counter in fills[side]
+  int stripe_cap[2];     // records per stripe
+  long long ovf_base[2]; // first record of the overflow segment (= nstripes * stripe_cap)
+  long long ovf_cap[2];  // its capacity
   int write_side[2];     // 0: global border, escapees are only counted
   int retire_batch;      // retire / refill once this many lanes of a warp are without a live
                          // history (>= 1): amortises the bookkeeping over short segments
@@ -102,6 +107,14 @@ cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsig
                                   int nstripes, int stripe_cap, long long ovf_base,
                                   unsigned long long *settled, long long settled_n,
                                   unsigned long long *out_total, cudaStream_t stream);
+
+// same packing, but from an INBOX (stripes filled by a neighbour's tracking kernel) straight
+// into the bank layout behind `bank_n` particles; *out_total = number of particles added
+cudaError_t launch_gather_stripes_to_bank(const unsigned long long *scratch,
+                                          const unsigned *fills, int nstripes, int stripe_cap,
+                                          long long ovf_base, unsigned long long *bank_seed,
+                                          float4 *bank_st, long long bank_n,
+                                          unsigned long long *out_total, cudaStream_t stream);
 
 // device-side birth (src/layer.cpp:101-120): particle i of the batch gets
 // seed = rnd_seed^(i+1)(chain_state), mu from the first rnd_real draw

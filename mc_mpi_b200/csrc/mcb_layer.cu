@@ -95,6 +95,16 @@ struct mcb200_layer {
   unsigned long long *d_scratch[2] = {nullptr, nullptr};  // per-launch stripes + overflow
   long long scratch_cap[2] = {0, 0};
   unsigned *d_stripe_n = nullptr;                         // [2][kStripes + 1]
+  // direct peer exchange: this layer's inbox (4 slots: from-side x parity) and the
+  // neighbours' inboxes this layer's kernel stores into
+  unsigned char *d_inbox = nullptr;
+  mcb200_inbox_geom inbox_geom{};
+  struct Peer {
+    unsigned char *base = nullptr;  // the neighbour's inbox block, mapped into this process
+    bool ipc = false;               // opened with cudaIpcOpenMemHandle (close on destroy)
+    mcb200_inbox_geom geom{};
+  } peer[2];
+  int parity = 0;
   mcb::CellXs *d_xs = nullptr;
   unsigned *d_acc = nullptr;          // u64[2][m + kAccExtra], see mcb_kernels.cu gacc_add
   mcb::DevCounters *d_ctr = nullptr;
@@ -254,6 +264,12 @@ int track(mcb200_layer *l, long long take) {
   const long long ovf_base = (long long)grid * stripe_cap;
   for (int s = 0; s < 2; ++s) {
     if (!write_side[s]) continue;
+    if (l->peer[s].base) {
+      // direct peer exchange: the stripes live in the neighbour's inbox, with ITS geometry
+      if (grid > l->peer[s].geom.nstripes || take > l->peer[s].geom.max_take)
+        return fail(MCB200_ERR_CAPACITY, "internal: launch does not fit the peer's inbox");
+      continue;
+    }
     int rc = rec_reserve(l, &l->d_scratch[s], &l->scratch_cap[s], 0, ovf_base + take);
     if (rc) return rc;
     rc = rec_reserve(l, &l->d_out[s], &l->out_cap[s], l->n_out[s], l->n_out[s] + take);
@@ -276,13 +292,26 @@ int track(mcb200_layer *l, long long take) {
   p.minw = l->particle_min_weight;
   p.acc = l->d_acc;
   for (int s = 0; s < 2; ++s) {
-    p.out_rec[s] = l->d_scratch[s];
     p.write_side[s] = write_side[s] ? 1 : 0;
+    if (write_side[s] && l->peer[s].base) {
+      // escapees on side s land in the neighbour's inbox slot "from side 1-s", this parity
+      const mcb200_inbox_geom &g = l->peer[s].geom;
+      unsigned char *slot = l->peer[s].base + (size_t)((1 - s) * 2 + l->parity) * (size_t)g.slot_bytes;
+      p.out_rec[s] = reinterpret_cast<unsigned long long *>(slot);
+      p.fills[s] = reinterpret_cast<unsigned *>(slot + g.fills_offset);
+      p.ovf_slot[s] = g.nstripes;
+      p.stripe_cap[s] = g.stripe_cap;
+      p.ovf_base[s] = (long long)g.nstripes * g.stripe_cap;
+      p.ovf_cap[s] = g.ovf_cap;
+    } else {
+      p.out_rec[s] = l->d_scratch[s];
+      p.fills[s] = l->d_stripe_n + s * (mcb::kStripes + 1);
+      p.ovf_slot[s] = grid;
+      p.stripe_cap[s] = stripe_cap;
+      p.ovf_base[s] = ovf_base;
+      p.ovf_cap[s] = take;
+    }
   }
-  p.stripe_n = l->d_stripe_n;
-  p.stripe_cap = stripe_cap;
-  p.ovf_base = ovf_base;
-  p.ovf_cap = take;
   p.ctr = l->d_ctr;
   // short segments (thin sub-slabs of a multi-GPU run) retire often: batch the bookkeeping
   p.retire_batch = l->opt_retire_batch > 0 ? l->opt_retire_batch : (l->m < 512 ? 4 : 2);
@@ -291,7 +320,7 @@ int track(mcb200_layer *l, long long take) {
   MCB_CUDA(mcb::launch_track(p, l->cfg, l->stream));
   MCB_CUDA(cudaEventRecord(l->ev1, l->stream));
   for (int s = 0; s < 2; ++s) {
-    if (!write_side[s]) continue;
+    if (!write_side[s] || l->peer[s].base) continue;  // peer sides: already delivered
     MCB_CUDA(mcb::launch_gather_stripes(l->d_scratch[s],
                                         l->d_stripe_n + s * (mcb::kStripes + 1), grid, stripe_cap,
                                         ovf_base, l->d_out[s], l->n_out[s],
@@ -512,6 +541,9 @@ void mcb200_layer_destroy(mcb200_layer *l) {
       cudaFree(l->d_scratch[s]);
     }
     cudaFree(l->d_stripe_n);
+    for (int s = 0; s < 2; ++s)
+      if (l->peer[s].base && l->peer[s].ipc) cudaIpcCloseMemHandle(l->peer[s].base);
+    cudaFree(l->d_inbox);
     cudaFree(l->d_xs);
     cudaFree(l->d_acc);
     cudaFree(l->d_ctr);
@@ -642,6 +674,13 @@ int mcb200_layer_simulate(mcb200_layer *l, int64_t nb_particles, mcb200_counts *
   if (!g.ok) return fail(MCB200_ERR_CUDA, "simulate: cudaSetDevice failed");
   long long want = nb_particles < 0 ? l->n_bank + l->n_unborn : (long long)nb_particles;
   if (want > l->n_bank + l->n_unborn) want = l->n_bank + l->n_unborn;
+  // with a neighbour's inbox connected, one call = ONE launch (a second launch of the same
+  // parity would overwrite the stripes of the first): the rest stays banked for the next cycle
+  for (int s = 0; s < 2; ++s)
+    if (l->peer[s].base) {
+      if (want > l->peer[s].geom.max_take) want = l->peer[s].geom.max_take;
+      if (want > l->opt_birth_chunk) want = l->opt_birth_chunk;
+    }
   while (want > 0) {
     // src/layer.cpp:244-245: births top the bank up when it holds fewer than asked
     if (l->n_bank < want && l->n_unborn > 0) {
@@ -654,6 +693,8 @@ int mcb200_layer_simulate(mcb200_layer *l, int64_t nb_particles, mcb200_counts *
     long long take = want < l->n_bank ? want : l->n_bank;
     // keep launches bounded by the birth chunk so outboxes stay bounded too
     if (take > l->opt_birth_chunk) take = l->opt_birth_chunk;
+    for (int s = 0; s < 2; ++s)  // a connected neighbour's inbox bounds one launch
+      if (l->peer[s].base && take > l->peer[s].geom.max_take) take = l->peer[s].geom.max_take;
     if (take <= 0) break;
     int rc = track(l, take);
     if (rc) return rc;
@@ -690,6 +731,127 @@ int mcb200_layer_pop_right_device(mcb200_layer *l, void *dev_aos, int64_t cap, i
   int rc = pop_side(l, 1, dev_aos, true, cap, &n);
   if (n_out) *n_out = n;
   return rc;
+}
+
+int mcb200_layer_inbox_create(mcb200_layer *l, int64_t max_take,
+                              uint8_t handle_out[MCB200_IPC_HANDLE_BYTES],
+                              mcb200_inbox_geom *geom_out) {
+  if (!l || max_take <= 0 || !geom_out)
+    return fail(MCB200_ERR_INVALID, "inbox_create: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MCB200_IPC_HANDLE_BYTES, "IPC handle size");
+  DeviceGuard g(l->device);
+  if (l->d_inbox) return fail(MCB200_ERR_INVALID, "inbox_create: the layer already has an inbox");
+  cudaDeviceProp prop;
+  MCB_CUDA(cudaGetDeviceProperties(&prop, l->device));
+  mcb200_inbox_geom q{};
+  // senders run the same kernel: at most 4 CTAs of 256 threads per SM (track_configure)
+  q.nstripes = prop.multiProcessorCount * 4;
+  if (q.nstripes > mcb::kStripes) q.nstripes = mcb::kStripes;
+  q.stripe_cap = (int32_t)(2 * ((max_take + q.nstripes - 1) / q.nstripes) + 64);
+  q.ovf_cap = max_take;
+  q.max_take = max_take;
+  const size_t rec_bytes =
+      ((size_t)q.nstripes * (size_t)q.stripe_cap + (size_t)q.ovf_cap) * sizeof(mcb200_particle);
+  q.fills_offset = (int64_t)((rec_bytes + 255) / 256 * 256);
+  q.slot_bytes =
+      q.fills_offset + (int64_t)(((size_t)(q.nstripes + 1) * sizeof(unsigned) + 255) / 256 * 256);
+  MCB_CUDA(cudaMalloc(&l->d_inbox, 4 * (size_t)q.slot_bytes));
+  // only the fill counters need to start at zero
+  for (int s = 0; s < 4; ++s)
+    MCB_CUDA(cudaMemsetAsync(l->d_inbox + (size_t)s * (size_t)q.slot_bytes + q.fills_offset, 0,
+                             (size_t)(q.nstripes + 1) * sizeof(unsigned), l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  l->inbox_geom = q;
+  *geom_out = q;
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    MCB_CUDA(cudaIpcGetMemHandle(&h, l->d_inbox));
+    std::memcpy(handle_out, &h, sizeof h);
+  }
+  return MCB200_OK;
+}
+
+int mcb200_layer_connect_peer(mcb200_layer *l, int32_t side,
+                              const uint8_t handle[MCB200_IPC_HANDLE_BYTES],
+                              const mcb200_inbox_geom *geom) {
+  if (!l || side < 0 || side > 1 || !handle || !geom)
+    return fail(MCB200_ERR_INVALID, "connect_peer: bad argument");
+  DeviceGuard g(l->device);
+  if (l->peer[side].base) return fail(MCB200_ERR_INVALID, "connect_peer: side already connected");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof h);
+  void *p = nullptr;
+  MCB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  l->peer[side].base = static_cast<unsigned char *>(p);
+  l->peer[side].ipc = true;
+  l->peer[side].geom = *geom;
+  return MCB200_OK;
+}
+
+int mcb200_layer_connect_local(mcb200_layer *l, int32_t side, mcb200_layer *other) {
+  if (!l || side < 0 || side > 1 || !other || !other->d_inbox)
+    return fail(MCB200_ERR_INVALID, "connect_local: bad argument (the neighbour needs an inbox)");
+  if (l->peer[side].base) return fail(MCB200_ERR_INVALID, "connect_local: side already connected");
+  if (other->device != l->device) {
+    DeviceGuard g(l->device);
+    int can = 0;
+    MCB_CUDA(cudaDeviceCanAccessPeer(&can, l->device, other->device));
+    if (!can) return fail(MCB200_ERR_CUDA, "connect_local: no peer access between the devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+      return fail(MCB200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+  }
+  l->peer[side].base = other->d_inbox;
+  l->peer[side].ipc = false;
+  l->peer[side].geom = other->inbox_geom;
+  return MCB200_OK;
+}
+
+int mcb200_layer_disconnect_peers(mcb200_layer *l) {
+  if (!l) return fail(MCB200_ERR_INVALID, "disconnect_peers: null layer");
+  DeviceGuard g(l->device);
+  if (l->stream) cudaStreamSynchronize(l->stream);
+  for (int s = 0; s < 2; ++s) {
+    if (l->peer[s].base && l->peer[s].ipc) cudaIpcCloseMemHandle(l->peer[s].base);
+    l->peer[s] = mcb200_layer::Peer{};
+  }
+  return MCB200_OK;
+}
+
+int mcb200_layer_set_exchange_parity(mcb200_layer *l, int32_t parity) {
+  if (!l || parity < 0 || parity > 1)
+    return fail(MCB200_ERR_INVALID, "set_exchange_parity: bad argument");
+  l->parity = parity;
+  return MCB200_OK;
+}
+
+int mcb200_layer_ingest_inbox(mcb200_layer *l, int32_t from_side, int32_t parity, int64_t *n_out) {
+  if (!l || from_side < 0 || from_side > 1 || parity < 0 || parity > 1 || !l->d_inbox)
+    return fail(MCB200_ERR_INVALID, "ingest_inbox: bad argument (no inbox?)");
+  DeviceGuard g(l->device);
+  const mcb200_inbox_geom &q = l->inbox_geom;
+  int rc = soa_reserve(l, &l->bank, l->n_bank, l->n_bank + q.max_take);
+  if (rc) return rc;
+  unsigned char *slot = l->d_inbox + (size_t)(from_side * 2 + parity) * (size_t)q.slot_bytes;
+  unsigned *fills = reinterpret_cast<unsigned *>(slot + q.fills_offset);
+  MCB_CUDA(cudaMemsetAsync(&l->d_ctr->out_total[0], 0, sizeof(unsigned long long), l->stream));
+  MCB_CUDA(mcb::launch_gather_stripes_to_bank(
+      reinterpret_cast<const unsigned long long *>(slot), fills, q.nstripes, q.stripe_cap,
+      (long long)q.nstripes * q.stripe_cap, l->bank.seed, l->bank.st, l->n_bank,
+      &l->d_ctr->out_total[0], l->stream));
+  l->gpu_launches++;
+  // the slot is written again two cycles from now: its fill counters must be zero by then
+  MCB_CUDA(cudaMemsetAsync(fills, 0, (size_t)(q.nstripes + 1) * sizeof(unsigned), l->stream));
+  unsigned long long n = 0;
+  MCB_CUDA(cudaMemcpyAsync(&n, &l->d_ctr->out_total[0], sizeof n, cudaMemcpyDeviceToHost,
+                           l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  if ((long long)n > q.max_take)
+    return fail(MCB200_ERR_CAPACITY, "ingest_inbox: the inbox was over-filled");
+  l->n_bank += (long long)n;
+  if (n_out) *n_out = (int64_t)n;
+  return MCB200_OK;
 }
 
 int mcb200_layer_outbox_device(mcb200_layer *l, int32_t side, void **dev_aos_out, int64_t *n_out) {

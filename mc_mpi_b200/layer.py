@@ -141,6 +141,35 @@ class Layer:
     def outbox_clear(self, side: int):
         check(_abi.lib().mcb200_layer_outbox_clear(self._h, int(side)))
 
+    # -- direct peer exchange over NVLink (mcb200.h) --
+    def inbox_create(self, max_take: int):
+        """allocate this layer's inbox; -> (IPC handle bytes, geometry bytes) for the peers"""
+        handle = (C.c_uint8 * _abi.IPC_HANDLE_BYTES)()
+        geom = _abi.InboxGeom()
+        check(_abi.lib().mcb200_layer_inbox_create(self._h, int(max_take), handle, C.byref(geom)))
+        return bytes(handle), bytes(geom)
+
+    def connect_peer(self, side: int, handle: bytes, geom: bytes):
+        """route escapees on `side` into the inbox of a neighbour living in another process"""
+        h = (C.c_uint8 * _abi.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        g = _abi.InboxGeom.from_buffer_copy(geom)
+        check(_abi.lib().mcb200_layer_connect_peer(self._h, int(side), h, C.byref(g)))
+
+    def connect_local(self, side: int, other: "Layer"):
+        """same, the neighbour being a layer of this process"""
+        check(_abi.lib().mcb200_layer_connect_local(self._h, int(side), other._h))
+
+    def disconnect_peers(self):
+        check(_abi.lib().mcb200_layer_disconnect_peers(self._h))
+
+    def set_exchange_parity(self, parity: int):
+        check(_abi.lib().mcb200_layer_set_exchange_parity(self._h, int(parity)))
+
+    def ingest_inbox(self, from_side: int, parity: int) -> int:
+        n = C.c_int64(0)
+        check(_abi.lib().mcb200_layer_ingest_inbox(self._h, int(from_side), int(parity), C.byref(n)))
+        return n.value
+
     @property
     def weights_absorbed(self) -> np.ndarray:
         out = np.empty(self.m, dtype=np.float32)

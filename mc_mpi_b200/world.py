@@ -61,7 +61,7 @@ def balanced_cuts(cuts, cost_per_rank, nb_cells, min_cells=8):
 class SlabWorld:
     def __init__(self, cfg: _configs.SlabConfig, *, rank=None, world_size=None, device=None,
                  nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True,
-                 cuts=None, ramp_from=None, overlap=True):
+                 cuts=None, ramp_from=None, overlap=False, transport="nccl"):
         self.cfg = cfg
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -84,6 +84,12 @@ class SlabWorld:
         self.on_device = isinstance(layer, Layer) and dist.get_backend(group) == "nccl"
         self.tdev = torch.device("cuda", layer.device) if self.on_device else torch.device("cpu")
         self.overlap = bool(overlap)
+        # "nccl": outbox -> ncclSend/Recv -> bank.  "p2p": the tracking kernel stores escapees
+        # straight into the neighbour GPU's inbox over NVLink (CUDA IPC mapping); per cycle
+        # only the small all-gather of the disabled counts remains as communication call.
+        self.transport = transport if self.on_device else "nccl"
+        if self.transport == "p2p":
+            self._connect_p2p()
         self._buf = {}
         self.cycles = 0
         self.migrations_out = 0
@@ -104,8 +110,36 @@ class SlabWorld:
     def recut(self, cuts):
         """move the sub-slab boundaries (between runs: the layer is rebuilt, tallies reset)"""
         self.cuts = list(cuts)
+        if self.transport == "p2p":
+            # nobody may free an inbox that a neighbour still has mapped
+            self.layer.disconnect_peers()
+            dist.barrier(group=self.group)
         self.layer.close()
         self.layer = self._make_layer()
+        if self.transport == "p2p":
+            self._connect_p2p()
+
+    def close(self):
+        if self.transport == "p2p":
+            self.layer.disconnect_peers()
+            dist.barrier(group=self.group)
+        self.layer.close()
+
+    def _connect_p2p(self):
+        """every rank allocates an inbox, the IPC handles go round with one all-gather, and each
+        layer maps its two neighbours' inboxes (the RmaComm window set-up, src/rma_comm.cpp:49-121)"""
+        K, r = self.world_size, self.rank
+        handle, geom = self.layer.inbox_create(self.per_cycle + self.per_cycle // 4)
+        blob = np.frombuffer(handle + geom, dtype=np.uint8)
+        mine = torch.from_numpy(blob.copy()).to(self.tdev)
+        table = torch.empty(K * mine.numel(), dtype=torch.uint8, device=self.tdev)
+        dist.all_gather_into_tensor(table, mine, group=self.group)
+        table = table.cpu().numpy().reshape(K, -1)
+        for side, peer in ((0, r - 1), (1, r + 1)):
+            if 0 <= peer < K:
+                raw = table[peer].tobytes()
+                self.layer.connect_peer(side, raw[: len(handle)], raw[len(handle):])
+        dist.barrier(group=self.group)
 
     # -- buffers ---------------------------------------------------------------------
     def _buffer(self, name: str, n_records: int) -> torch.Tensor:
@@ -192,9 +226,16 @@ class SlabWorld:
         total = self.cfg.nb_particles
         births = min(self.ramp_from, self.per_cycle) if self.ramp_from else self.per_cycle
         pending = None
+        p2p = self.transport == "p2p"
+        seen = self.layer.counts() if p2p else None
         while self.cycles < max_cycles:
             t0 = time.perf_counter()
             ta = t0
+            if p2p:
+                # escapees of this cycle are stored by the kernel into the neighbours' inboxes
+                # of this parity; the all-gather below doubles as the barrier after which they
+                # may be ingested
+                self.layer.set_exchange_parity(self.cycles & 1)
             if self.ramp_from:
                 # everything received so far + this cycle's share of the source
                 st = self.layer.counts()
@@ -208,14 +249,26 @@ class SlabWorld:
             t1 = time.perf_counter()
             table = self._gather_counts(c)
             tb = time.perf_counter()
-            # the previous cycle's transfers ran under this cycle's tracking
-            self._finish_exchange(pending)
-            tc = time.perf_counter()
-            pending = self._start_exchange(table, self.cycles & 1)
-            td = time.perf_counter()
-            if not self.overlap:
+            if p2p:
+                tc = tb
+                for from_side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
+                    if 0 <= peer < self.world_size:
+                        self.layer.ingest_inbox(from_side, self.cycles & 1)
+                td = time.perf_counter()
+                self.migrations_out += sum(
+                    c[k] - seen[k] for k, border in (("n_left", self.layer.left_border),
+                                                     ("n_right", self.layer.right_border))
+                    if not border)
+                seen = c
+            else:
+                # the previous cycle's transfers ran under this cycle's tracking
                 self._finish_exchange(pending)
-                pending = None
+                tc = time.perf_counter()
+                pending = self._start_exchange(table, self.cycles & 1)
+                td = time.perf_counter()
+                if not self.overlap:
+                    self._finish_exchange(pending)
+                    pending = None
             t2 = time.perf_counter()
             self.t_simulate += t1 - t0
             self.t_exchange += t2 - t1

@@ -242,6 +242,54 @@ def test_global_dx_decomposition_equals_single_layer(gpu):
             l.close()
 
 
+@pytest.mark.parametrize("K,per_cycle", [(3, 3000), (8, 100_000)])
+def test_direct_peer_exchange_on_one_gpu(gpu, K, per_cycle):
+    """The fused path: each layer's tracking kernel stores its escapees straight into the
+    neighbour layer's inbox (here all layers live on one GPU and are connected locally; across
+    GPUs the same pointers are CUDA-IPC mappings over NVLink).  Double-buffered by parity,
+    ingested after the cycle.  Must reproduce the single-layer run bit for bit."""
+    cfg = configs.reference_default(20_000)
+    with gpu_layer(cfg, keep_border=False) as one:
+        one.simulate(-1)
+        q1, _ = one.weights_absorbed_exact()
+        c1 = one.counts()
+    layers = [decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, K, r, cfg.nb_cells,
+                               cfg.nb_particles, cfg.particle_min_weight, global_dx=True)
+              for r in range(K)]
+    for l in layers:
+        l.inbox_create(per_cycle)
+    for r, l in enumerate(layers):
+        if r > 0:
+            l.connect_local(0, layers[r - 1])
+        if r + 1 < K:
+            l.connect_local(1, layers[r + 1])
+    cycles = 0
+    while sum(l.nb_disabled for l in layers) < cfg.nb_particles:
+        parity = cycles & 1
+        for l in layers:
+            l.set_exchange_parity(parity)
+            l.simulate(per_cycle)                   # at most one launch: the inbox bounds it
+        received = 0
+        for r, l in enumerate(layers):
+            if r > 0:
+                received += l.ingest_inbox(0, parity)
+            if r + 1 < K:
+                received += l.ingest_inbox(1, parity)
+        cycles += 1
+        assert cycles < 10_000
+    assert all(l.counts()["n_outbox_left"] == 0 and l.counts()["n_outbox_right"] == 0 for l in layers)
+    qK = np.concatenate([l.weights_absorbed_exact()[0] for l in layers])
+    assert np.array_equal(qK, q1)
+    assert sum(l.counts()["events"] for l in layers) == c1["events"]
+    assert sum(l.counts()["scatters"] for l in layers) == c1["scatters"]
+    assert layers[0].counts()["n_left"] == c1["n_left"]
+    assert layers[-1].counts()["n_right"] == c1["n_right"]
+    for l in layers:
+        l.disconnect_peers()
+    for l in layers:
+        l.close()
+
+
 def test_full_size_properties(gpu):
     """BASELINE config 2 at full size (1e8 histories, 1000 cells): no oracle can follow, so
     size-independent properties: conservation, counts add up, the tally profile agrees with a

@@ -31,8 +31,9 @@ def main():
         edges = np.concatenate([[0], np.cumsum(wts / wts.sum() * cfg.nb_cells)]).round().astype(int)
         edges[-1] = cfg.nb_cells
         cuts = edges.tolist()
+    transport = sys.argv[5] if len(sys.argv) > 5 else "nccl"
     w = SlabWorld(cfg, device=local, nb_particles_per_cycle=per_cycle, cuts=cuts,
-                  ramp_from=(per_cycle // 8 or 1) if cuts else None)
+                  ramp_from=(per_cycle // 8 or 1) if cuts else None, transport=transport)
     s = w.spin()
     wa = w.gather_weights_absorbed()
     stats = torch.tensor([s["events"], s["scatters"], s["migrations_out"],
@@ -56,13 +57,14 @@ def main():
                   "max rel", float(np.max(np.abs(w1 - wa) / w1)) if len(bad) else 0.0,
                   "sum K", float(wa.sum()), "sum 1", float(w1.sum()))
         ok &= same_counts
-        print(f"[multi-gpu parity] cuts={w.cuts}")
+        print(f"[multi-gpu parity] cuts={w.cuts} transport={w.transport}")
         print(f"[multi-gpu parity] K={K} config={cfg.name} histories={n} cycles={s['cycles']} "
               f"migrations/history={mig / n:.3f} events={ev} tally_bit_exact={ok}", flush=True)
         one.close()
         if not ok:
             dist.destroy_process_group()
             sys.exit(1)
+    w.close()
     dist.destroy_process_group()
 
 
