@@ -400,7 +400,7 @@ def run_gpu_arm(args):
                                       f"({'cuts balanced on measured tracking time' if args.balance and args.warmup > 1 else 'equal cell counts'}), "
                                       f"<= {args.per_cycle} source histories per cycle, escapees "
                                       + ("stored by the tracking kernel into the neighbour GPU's "
-                                         "inbox over NVLink (CUDA IPC)" if args.transport == "p2p"
+                                         "inbox over NVLink (CUDA IPC)" if sw.transport == "p2p"
                                          else "shipped with ncclSend/Recv")},
             "events_per_s": events / (dev_ms * 1e-3),
             "wall_s": wall,
@@ -415,6 +415,7 @@ def run_gpu_arm(args):
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        sw.close()
         dist.destroy_process_group()
 
 
@@ -428,7 +429,7 @@ def main():
     ap.add_argument("--per-cycle", type=int, default=1 << 25, dest="per_cycle")
     ap.add_argument("--ramp-from", type=int, default=1 << 20, dest="ramp_from",
                     help="source histories of the first cycle (doubling up to --per-cycle); 0 = flat")
-    ap.add_argument("--transport", choices=["nccl", "p2p"], default="nccl",
+    ap.add_argument("--transport", choices=["nccl", "p2p"], default="p2p",
                     help="N > 1: nccl = outbox -> ncclSend/Recv -> bank; p2p = the tracking kernel "
                          "stores escapees straight into the neighbour GPU's inbox over NVLink")
     ap.add_argument("--overlap", action="store_true",

@@ -148,7 +148,7 @@ def main(argv=None) -> int:
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         sw = SlabWorld(cfg, device=local, nb_particles_per_cycle=opt["nb_particles_per_cycle"],
-                       ramp_from=min(1 << 20, opt["nb_particles_per_cycle"]))
+                       ramp_from=min(1 << 20, opt["nb_particles_per_cycle"]), transport="p2p")
         if opt["balance"]:
             # a short pilot run places the cuts where the measured tracking time balances
             pilot = cfg.with_particles(max(min(cfg.nb_particles // 20, 5_000_000), 1000))
@@ -174,6 +174,7 @@ def main(argv=None) -> int:
         lay0.dump_WA("WA.out")
     if world > 1:
         import torch.distributed as dist
+        sw.close()          # unmap the neighbours' inboxes before anybody frees one
         dist.barrier()
         dist.destroy_process_group()
     return 0

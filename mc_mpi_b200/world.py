@@ -128,17 +128,35 @@ class SlabWorld:
     def _connect_p2p(self):
         """every rank allocates an inbox, the IPC handles go round with one all-gather, and each
         layer maps its two neighbours' inboxes (the RmaComm window set-up, src/rma_comm.cpp:49-121)"""
+        from ._abi import IPC_HANDLE_BYTES, InboxGeom, McbError
+        import ctypes
         K, r = self.world_size, self.rank
-        handle, geom = self.layer.inbox_create(self.per_cycle + self.per_cycle // 4)
-        blob = np.frombuffer(handle + geom, dtype=np.uint8)
+        n_h, n_g = IPC_HANDLE_BYTES, ctypes.sizeof(InboxGeom)
+        ok = 1
+        try:
+            handle, geom = self.layer.inbox_create(self.per_cycle + self.per_cycle // 4)
+        except McbError:
+            ok, handle, geom = 0, bytes(n_h), bytes(n_g)
+        blob = np.frombuffer(handle + geom + bytes([ok]), dtype=np.uint8)
         mine = torch.from_numpy(blob.copy()).to(self.tdev)
         table = torch.empty(K * mine.numel(), dtype=torch.uint8, device=self.tdev)
         dist.all_gather_into_tensor(table, mine, group=self.group)
         table = table.cpu().numpy().reshape(K, -1)
-        for side, peer in ((0, r - 1), (1, r + 1)):
-            if 0 <= peer < K:
-                raw = table[peer].tobytes()
-                self.layer.connect_peer(side, raw[: len(handle)], raw[len(handle):])
+        ok = int(table[:, -1].min())
+        if ok:
+            try:
+                for side, peer in ((0, r - 1), (1, r + 1)):
+                    if 0 <= peer < K:
+                        raw = table[peer].tobytes()
+                        self.layer.connect_peer(side, raw[:n_h], raw[n_h:n_h + n_g])
+            except McbError:
+                ok = 0
+        # every rank must agree: one rank without peer access puts everybody back on NCCL
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.tdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.layer.disconnect_peers()
+            self.transport = "nccl"
         dist.barrier(group=self.group)
 
     # -- buffers ---------------------------------------------------------------------
