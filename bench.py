@@ -365,11 +365,31 @@ def run_gpu_arm(args):
                "interface": "mcb200_layer_push(host Particle[]) + mcb200_layer_simulate(-1) + "
                             "mcb200_layer_weights_absorbed (what Layer::simulate / cusimulate do)"}
         e_layer.close()
+    elif world > 1 and not args.no_e2e:
+        # N > 1: the public call sequence of a run -- register the source
+        # (Layer::create_particles takes scalars, no particle buffer), spin, gather the tally to
+        # the host like Worker::dump (src/worker.cpp:36-61) -- timed by the host clock, the
+        # read-back inside the timed region.  The host-BUFFER arm (24-byte Particle records
+        # pushed over PCIe) is what the N = 1 line measures.
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+            wa = sw.gather_weights_absorbed()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t)
+        import ctypes
+        e2e = {"value": n_hist * args.steps / dt, "unit": "histories/s",
+               "h2d_bytes_per_step": int(ctypes.sizeof(_abi.LayerDesc)),
+               "d2h_bytes_per_step": int(8 * cfg.nb_cells + world * ctypes.sizeof(_abi.Counts)),
+               "histories_per_step": n_hist,
+               "interface": "decompose_domain / create_particles (scalars) + SlabWorld.spin + "
+                            "gather_weights_absorbed to the host; host-buffer arm: see N = 1"}
+        if rank == 0:
+            assert wa is not None and float(wa.sum()) > 0
     elif world > 1:
         e2e = {"value": None, "unit": "histories/s", "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": 0,
-               "note": "multi-GPU run is device-resident (births on the source GPU, escapees "
-                       "GPU-to-GPU); the host-buffer arm is measured at N=1"}
+               "d2h_bytes_per_step": 0, "note": "--no-e2e"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
