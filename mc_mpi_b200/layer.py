@@ -61,6 +61,16 @@ class Layer:
                              if right_border is None else bool(right_border))
 
     # -- life cycle --
+    def clone(self) -> "Layer":
+        """deep copy, device state included (Layer is copied / returned by value in the
+        reference: src/layer.cpp:41, include/mcmpi/worker.hpp:60)"""
+        h = C.c_void_p()
+        check(_abi.lib().mcb200_layer_clone(self._h, C.byref(h)))
+        other = object.__new__(Layer)
+        other.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_h"})
+        other._h = h
+        return other
+
     def close(self):
         if self._h is not None:
             _abi.lib().mcb200_layer_destroy(self._h)

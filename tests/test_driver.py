@@ -44,7 +44,6 @@ def test_dump_formats(tmp_path):
     # YamlDumper formats (src/yaml_dumper.cpp:13-24): %d, %.18e
     assert "# Read from config\nnb_cells: 1000\nx_min: 0.000000000000000000e+00\n" in txt
     assert "x_ini: 7.071067690849304199e-01\n" in txt and "world_size: 5\n" in txt
-    again = load_config(str(tmp_path / "config.yaml")) if False else None  # comments are not keys
     w = np.linspace(1e-4, 2e-4, 10)
     dump_weights_absorbed(str(tmp_path / "weights.csv"), w, [0, 4, 10], np.float32(0.1))
     rows = (tmp_path / "weights.csv").read_text().splitlines()

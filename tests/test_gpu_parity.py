@@ -156,6 +156,27 @@ def test_partial_simulate_and_birth_chunks(gpu):
         assert_layer_matches_oracle(g, o)
 
 
+def test_clone_is_a_deep_copy(gpu):
+    """Layer is copy-constructed / returned by value in the reference (src/layer.cpp:41,
+    include/mcmpi/worker.hpp:60): a clone taken mid-run carries bank, outboxes, tally and the
+    unborn source, and both copies then finish identically to an uninterrupted run."""
+    cfg = configs.reference_default(6_000)
+    o = make_oracle(cfg, 5, 3)
+    o.simulate(-1)
+    a = decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, 5, 3, cfg.nb_cells, cfg.nb_particles,
+                         cfg.particle_min_weight)
+    a.simulate(2_500)
+    b = a.clone()
+    for g in (a, b):
+        g.simulate(-1)
+        assert np.array_equal(g.weights_absorbed_exact()[0], o.tally_exact)
+        c, st = g.counts(), o.stats()
+        assert (c["n_left"], c["n_right"], c["events"]) == (st["n_left"], st["n_right"], st["events"])
+        assert particles_equal(g.pop_left(), o.particles_left)
+        assert particles_equal(g.pop_right(), o.particles_right)
+        g.close()
+
+
 def test_push_pop_roundtrip_and_edge_cases(gpu):
     cfg = configs.reference_default(1000)
     start, m = split_cells(cfg.nb_cells, 4, 1)
