@@ -97,6 +97,18 @@ def dump_weights_absorbed(path: str, weights: np.ndarray, cuts, dx: np.float32) 
             f.write(f"{proc}, {float(dx) * (i + 0.5):.18e}, {float(w32[i] / dx):.18e}\n")
 
 
+def dump_stats(path: str, rows_by_rank) -> None:
+    """Worker::write_file (src/worker.cpp:63-181) with Timer::State's formats (src/timer.cpp:41-53):
+    `rank, starttime, endtime, time_comp, time_send, time_recv, time_idle, nb_cycles, ` -- one row
+    per rank and statistics window.  nb_cycles counts the terminating cycle too (the reference
+    breaks out just before its counter)."""
+    with open(path, "w") as f:
+        f.write("rank, starttime, endtime, time_comp, time_send, time_recv, time_idle, nb_cycles, \n")
+        for rank, rows in enumerate(rows_by_rank):
+            for row in rows:
+                f.write(f"{rank}, " + "".join(f"{v:.18e}, " for v in row[:6]) + f"{int(row[6])}, \n")
+
+
 def slab_config(opt: dict) -> _configs.SlabConfig:
     def table(path):
         if not path:
@@ -136,10 +148,11 @@ def main(argv=None) -> int:
                                  cfg.nb_particles, cfg.particle_min_weight, device=local,
                                  sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        t0, w0 = time.perf_counter(), time.time()
         layer.simulate(-1)                      # Worker::spin
         elapsed = time.perf_counter() - t0
         weights, cuts, lay0 = layer.weights_absorbed_f64, [0, cfg.nb_cells], layer
+        stat_rows = [[(w0, w0 + elapsed, elapsed, 0.0, 0.0, 0.0, 1)]]
     else:
         import torch.distributed as dist
 
@@ -148,7 +161,8 @@ def main(argv=None) -> int:
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         sw = SlabWorld(cfg, device=local, nb_particles_per_cycle=opt["nb_particles_per_cycle"],
-                       ramp_from=min(1 << 20, opt["nb_particles_per_cycle"]), transport="p2p")
+                       ramp_from=min(1 << 20, opt["nb_particles_per_cycle"]), transport="p2p",
+                       statistics_cycle_time=opt["statistics_cycle_time"] or 1e30)
         if opt["balance"]:
             # a short pilot run places the cuts where the measured tracking time balances
             pilot = cfg.with_particles(max(min(cfg.nb_particles // 20, 5_000_000), 1000))
@@ -166,11 +180,13 @@ def main(argv=None) -> int:
         dist.barrier()
         elapsed = time.perf_counter() - t0
         weights, cuts, lay0 = sw.gather_weights_absorbed(), sw.cuts, sw.layer
+        stat_rows = sw.gather_stat_rows()
     if rank == 0:
         print(f"{elapsed:f}")                   # main.cpp:91
         os.makedirs("out", exist_ok=True)       # Worker::dump, src/worker.cpp:36-61
         dump_config(os.path.join("out", "config.yaml"), opt, world)
         dump_weights_absorbed(os.path.join("out", "weights.csv"), weights, cuts, dx)
+        dump_stats(os.path.join("out", "stats.csv"), stat_rows)
         lay0.dump_WA("WA.out")
     if world > 1:
         import torch.distributed as dist

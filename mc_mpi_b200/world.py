@@ -58,11 +58,35 @@ def balanced_cuts(cuts, cost_per_rank, nb_cells, min_cells=8):
     return new + [nb_cells]
 
 
+class _StatWindow:
+    """one Timer::State: wall-clock start/end and the seconds spent per phase"""
+
+    def __init__(self):
+        self.start = time.time()
+        self.comp = self.send = self.recv = self.idle = 0.0
+        self.cycles = 0
+
+    def add(self, comp=0.0, send=0.0, recv=0.0, idle=0.0):
+        self.comp += comp
+        self.send += send
+        self.recv += recv
+        self.idle += idle
+        self.cycles += 1
+
+    def close(self):
+        return (self.start, time.time(), self.comp, self.send, self.recv, self.idle, self.cycles)
+
+
 class SlabWorld:
     def __init__(self, cfg: _configs.SlabConfig, *, rank=None, world_size=None, device=None,
                  nb_particles_per_cycle=1 << 23, layer=None, group=None, global_dx=True,
-                 cuts=None, ramp_from=None, overlap=False, transport="nccl"):
+                 cuts=None, ramp_from=None, overlap=False, transport="nccl",
+                 statistics_cycle_time=None):
         self.cfg = cfg
+        # Timer::State rows (include/timer/timer.hpp, src/worker_sync.cpp:122-139): one per
+        # `statistics_cycle_time` seconds of spin() plus the final one; None = no rows
+        self.statistics_cycle_time = statistics_cycle_time
+        self.stat_rows = []
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
@@ -246,6 +270,7 @@ class SlabWorld:
         pending = None
         p2p = self.transport == "p2p"
         seen = self.layer.counts() if p2p else None
+        stat = _StatWindow() if self.statistics_cycle_time is not None else None
         while self.cycles < max_cycles:
             t0 = time.perf_counter()
             ta = t0
@@ -300,13 +325,28 @@ class SlabWorld:
                                    int(table[self.rank, 0]), int(table[self.rank, 1]),
                                    c["n_bank"], c["n_unborn"]))
             self.cycles += 1
+            if stat is not None:
+                # Computation / Recv (events) / Send (particles), as the sync worker tags them
+                stat.add(comp=t1 - t0, recv=tb - t1, send=t2 - tb)
+                if time.time() > stat.start + self.statistics_cycle_time:
+                    self.stat_rows.append(stat.close())
+                    stat = _StatWindow()
             if int(table[:, 2].sum()) == total:
                 # every source particle is disabled somewhere: nothing can be in flight
                 self._finish_exchange(pending)
                 break
         else:
             raise RuntimeError("SlabWorld.spin: did not terminate")
+        if stat is not None:
+            self.stat_rows.append(stat.close())
         return self.summary()
+
+    def gather_stat_rows(self):
+        """Worker::write_file's gather (src/worker.cpp:63-181): every rank's rows on rank 0 as
+        a list indexed by rank (None elsewhere)"""
+        rows = [None] * self.world_size
+        dist.all_gather_object(rows, self.stat_rows, group=self.group)
+        return rows if self.rank == 0 else None
 
     # -- results ---------------------------------------------------------------------
     def summary(self) -> dict:

@@ -52,6 +52,69 @@ def test_dump_formats(tmp_path):
     assert re.fullmatch(r"\d+, \d\.\d{18}e[+-]\d\d, \d\.\d{18}e[+-]\d\d", rows[3])
 
 
+def test_dump_stats_has_the_reference_layout(tmp_path):
+    """same header and field formats as the reference program's out/stats.csv
+    (Worker::write_file, Timer::State::sprintf; an actual file is produced by ref_main_cpu in
+    tests/test_ref_program.py)"""
+    from mc_mpi_b200.main import dump_stats
+    dump_stats(str(tmp_path / "stats.csv"),
+               [[(10.0, 10.5, 0.25, 0.125, 0.0625, 0.0, 7)], [(10.0, 10.25, 0.1, 0.0, 0.0, 0.0, 3),
+                                                               (10.25, 10.5, 0.2, 0.0, 0.0, 0.0, 4)]])
+    rows = (tmp_path / "stats.csv").read_text().splitlines()
+    assert rows[0] == "rank, starttime, endtime, time_comp, time_send, time_recv, time_idle, nb_cycles, "
+    assert rows[1] == ("0, 1.000000000000000000e+01, 1.050000000000000000e+01, 2.500000000000000000e-01, "
+                       "1.250000000000000000e-01, 6.250000000000000000e-02, 0.000000000000000000e+00, 7, ")
+    assert [r.split(",")[0] for r in rows[1:]] == ["0", "1", "1"]
+
+
+def test_driver_single_rank_flow_with_a_stand_in_layer(tmp_path, monkeypatch):
+    """main()'s host flow for one rank -- config -> simulate(-1) -> one line + out/{config.yaml,
+    weights.csv,stats.csv} + WA.out -- with the oracle standing in for the GPU layer (the real
+    run is test_driver_end_to_end)"""
+    sys.path.insert(0, HERE)
+    import torch
+    from mc_mpi_b200 import layer as mcb_layer, main as mcb_main
+    from util import make_oracle
+
+    class StandIn:
+        def __init__(self, cfg):
+            self.o = make_oracle(cfg, keep_border=False)
+
+        def simulate(self, n):
+            self.o.simulate(n)
+
+        @property
+        def weights_absorbed_f64(self):
+            return self.o.tally_exact_f64
+
+        def dump_WA(self, path):
+            self.o.dump_WA(path)
+
+    made = []
+
+    def fake_decompose(x_min, x_max, x_ini, K, r, nb_cells, nb_particles, minw, **kw):
+        from mc_mpi_b200 import configs
+        made.append(StandIn(configs.SlabConfig("t", nb_cells, nb_particles, minw, x_min, x_max, x_ini)))
+        return made[-1]
+
+    monkeypatch.setattr(mcb_layer, "decompose_domain", fake_decompose)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.chdir(tmp_path)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    cfg_path = tmp_path / "config.yaml"
+    cfg_path.write_text(open(CONFIG).read().replace("nb_particles: 100000", "nb_particles: 2000"))
+    assert mcb_main.main([str(cfg_path)]) == 0
+    assert sorted(os.listdir(tmp_path / "out")) == ["config.yaml", "stats.csv", "weights.csv"]
+    assert (tmp_path / "WA.out").exists()
+    rows = np.loadtxt(tmp_path / "out" / "weights.csv", delimiter=",", skiprows=1)
+    dx = np.float32(1.0) / np.float32(1000)
+    assert np.allclose(rows[:, 2] * dx, made[0].o.tally_exact_f64, rtol=1e-6, atol=0)
+    stats = (tmp_path / "out" / "stats.csv").read_text().splitlines()
+    assert len(stats) == 2 and stats[1].startswith("0, ") and stats[1].endswith(", 1, ")
+
+
 @pytest.mark.gpu
 def test_driver_end_to_end(gpu, tmp_path):
     """`python -m mc_mpi_b200.main config.yaml`: one wall-time line; out/weights.csv equals the

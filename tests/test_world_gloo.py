@@ -63,11 +63,12 @@ def _worker(rank, K, port, n, per_cycle, overlap, q):
         from mc_mpi_b200.world import SlabWorld
         cfg = configs.reference_default(n)
         w = SlabWorld(cfg, nb_particles_per_cycle=per_cycle, layer=OracleAsLayer(cfg, K, rank),
-                      global_dx=False, overlap=overlap)
+                      global_dx=False, overlap=overlap, statistics_cycle_time=1e-3)
         s = w.spin()
         wa = w.gather_weights_absorbed()
+        stats = w.gather_stat_rows()
         q.put((rank, s["cycles"], s["migrations_out"], s["nb_disabled"], s["events"],
-               None if wa is None else wa.tolist()))
+               None if wa is None else wa.tolist(), stats))
     finally:
         dist.destroy_process_group()
 
@@ -110,3 +111,13 @@ def test_slab_world_over_gloo(K, n, per_cycle, overlap):
     assert [r[4] for r in res] == [l.stats()["events"] for l in layers]
     assert np.array_equal(np.array(res[0][5]), want_wa)         # gathered tally, rank 0
     assert all(r[5] is None for r in res[1:])
+    # Timer::State rows (stats.csv): on rank 0 one list per rank, windows contiguous in time,
+    # cycles adding up, phases inside the window
+    stats = res[0][6]
+    assert all(r[6] is None for r in res[1:]) and len(stats) == K
+    for rows in stats:
+        assert sum(row[6] for row in rows) == res[0][1]
+        for row in rows:
+            start, end, comp, send, recv, idle, _ = row
+            assert end >= start and min(comp, send, recv) >= 0 and idle == 0
+            assert comp + send + recv <= (end - start) + 1e-3
