@@ -52,6 +52,16 @@ struct DeviceGuard {
   }
 };
 
+// scratch device allocation of the known-answer-test entry points: freed on every return path
+template <typename T>
+struct DevScratch {
+  T *p = nullptr;
+  ~DevScratch() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+};
+
 // growable pair of device arrays in the bank layout
 struct SoaBuf {
   unsigned long long *seed = nullptr;
@@ -143,11 +153,17 @@ int soa_reserve(mcb200_layer *l, SoaBuf *b, long long used, long long want) {
     return fail(MCB200_ERR_NOMEM, std::string("cudaMalloc bank: ") + cudaGetErrorString(e));
   }
   if (used > 0) {
-    MCB_CUDA(cudaMemcpyAsync(ns, b->seed, (size_t)used * sizeof(unsigned long long),
-                             cudaMemcpyDeviceToDevice, l->stream));
-    MCB_CUDA(cudaMemcpyAsync(nt, b->st, (size_t)used * sizeof(float4), cudaMemcpyDeviceToDevice,
-                             l->stream));
-    MCB_CUDA(cudaStreamSynchronize(l->stream));
+    e = cudaMemcpyAsync(ns, b->seed, (size_t)used * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToDevice, l->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(nt, b->st, (size_t)used * sizeof(float4), cudaMemcpyDeviceToDevice,
+                          l->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(l->stream);
+    if (e != cudaSuccess) {
+      cudaFree(ns);
+      cudaFree(nt);
+      return fail(MCB200_ERR_CUDA, std::string("growing the bank: ") + cudaGetErrorString(e));
+    }
   }
   cudaFree(b->seed);
   cudaFree(b->st);
@@ -166,9 +182,13 @@ int rec_reserve(mcb200_layer *l, unsigned long long **buf, long long *cap, long 
   unsigned long long *nb = nullptr;
   MCB_CUDA(cudaMalloc(&nb, (size_t)nc * sizeof(mcb200_particle)));
   if (used > 0) {
-    MCB_CUDA(cudaMemcpyAsync(nb, *buf, (size_t)used * sizeof(mcb200_particle),
-                             cudaMemcpyDeviceToDevice, l->stream));
-    MCB_CUDA(cudaStreamSynchronize(l->stream));
+    cudaError_t e = cudaMemcpyAsync(nb, *buf, (size_t)used * sizeof(mcb200_particle),
+                                    cudaMemcpyDeviceToDevice, l->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(l->stream);
+    if (e != cudaSuccess) {
+      cudaFree(nb);
+      return fail(MCB200_ERR_CUDA, std::string("growing an outbox: ") + cudaGetErrorString(e));
+    }
   }
   cudaFree(*buf);
   *buf = nb;
@@ -466,6 +486,8 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
   if (d->abi_version != MCB200_ABI_VERSION)
     return fail(MCB200_ERR_INVALID, "create: abi_version mismatch");
   if (d->m <= 0) return fail(MCB200_ERR_INVALID, "create: m must be positive");
+  if (!(d->x_max > d->x_min) || !std::isfinite(d->x_min) || !std::isfinite(d->x_max))
+    return fail(MCB200_ERR_INVALID, "create: need finite x_min < x_max");
   int ndev = 0;
   MCB_CUDA(cudaGetDeviceCount(&ndev));
   if (d->device < 0 || d->device >= ndev)
@@ -756,12 +778,12 @@ int mcb200_layer_inbox_create(mcb200_layer *l, int64_t max_take,
   q.slot_bytes =
       q.fills_offset + (int64_t)(((size_t)(q.nstripes + 1) * sizeof(unsigned) + 255) / 256 * 256);
   MCB_CUDA(cudaMalloc(&l->d_inbox, 4 * (size_t)q.slot_bytes));
+  l->inbox_geom = q;
   // only the fill counters need to start at zero
   for (int s = 0; s < 4; ++s)
     MCB_CUDA(cudaMemsetAsync(l->d_inbox + (size_t)s * (size_t)q.slot_bytes + q.fills_offset, 0,
                              (size_t)(q.nstripes + 1) * sizeof(unsigned), l->stream));
   MCB_CUDA(cudaStreamSynchronize(l->stream));
-  l->inbox_geom = q;
   *geom_out = q;
   if (handle_out) {
     cudaIpcMemHandle_t h;
@@ -940,16 +962,14 @@ int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host, int6
   if (n == 0) return MCB200_OK;
   DeviceGuard g(device);
   if (!g.ok) return fail(MCB200_ERR_CUDA, "test_rnd_real: cudaSetDevice failed");
-  unsigned long long *ds = nullptr;
-  float *dout = nullptr;
-  MCB_CUDA(cudaMalloc(&ds, (size_t)n * 8));
-  MCB_CUDA(cudaMalloc(&dout, (size_t)n * 4));
-  MCB_CUDA(cudaMemcpy(ds, seeds_host, (size_t)n * 8, cudaMemcpyHostToDevice));
-  MCB_CUDA(mcb::launch_test_rnd_real(n, ds, dout, nullptr));
-  MCB_CUDA(cudaMemcpy(seeds_host, ds, (size_t)n * 8, cudaMemcpyDeviceToHost));
-  MCB_CUDA(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  cudaFree(ds);
-  cudaFree(dout);
+  DevScratch<unsigned long long> ds;
+  DevScratch<float> dout;
+  MCB_CUDA(ds.alloc((size_t)n));
+  MCB_CUDA(dout.alloc((size_t)n));
+  MCB_CUDA(cudaMemcpy(ds.p, seeds_host, (size_t)n * 8, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_rnd_real(n, ds.p, dout.p, nullptr));
+  MCB_CUDA(cudaMemcpy(seeds_host, ds.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  MCB_CUDA(cudaMemcpy(out_host, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return MCB200_OK;
 }
 
@@ -959,14 +979,12 @@ static int test_math(int which, int device, const float *in_host, float *out_hos
   if (n == 0) return MCB200_OK;
   DeviceGuard g(device);
   if (!g.ok) return fail(MCB200_ERR_CUDA, "test_math: cudaSetDevice failed");
-  float *din = nullptr, *dout = nullptr;
-  MCB_CUDA(cudaMalloc(&din, (size_t)n * 4));
-  MCB_CUDA(cudaMalloc(&dout, (size_t)n * 4));
-  MCB_CUDA(cudaMemcpy(din, in_host, (size_t)n * 4, cudaMemcpyHostToDevice));
-  MCB_CUDA(mcb::launch_test_math(which, n, din, dout, nullptr));
-  MCB_CUDA(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  cudaFree(din);
-  cudaFree(dout);
+  DevScratch<float> din, dout;
+  MCB_CUDA(din.alloc((size_t)n));
+  MCB_CUDA(dout.alloc((size_t)n));
+  MCB_CUDA(cudaMemcpy(din.p, in_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_math(which, n, din.p, dout.p, nullptr));
+  MCB_CUDA(cudaMemcpy(out_host, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return MCB200_OK;
 }
 int mcb200_test_logf(int device, const float *in_host, float *out_host, int64_t n) {
@@ -983,17 +1001,14 @@ int mcb200_test_edge_distance(int device, const float *a_host, const float *mu_h
   if (n == 0) return MCB200_OK;
   DeviceGuard g(device);
   if (!g.ok) return fail(MCB200_ERR_CUDA, "test_edge_distance: cudaSetDevice failed");
-  float *da = nullptr, *db = nullptr, *dout = nullptr;
-  MCB_CUDA(cudaMalloc(&da, (size_t)n * 4));
-  MCB_CUDA(cudaMalloc(&db, (size_t)n * 4));
-  MCB_CUDA(cudaMalloc(&dout, (size_t)n * 4));
-  MCB_CUDA(cudaMemcpy(da, a_host, (size_t)n * 4, cudaMemcpyHostToDevice));
-  MCB_CUDA(cudaMemcpy(db, mu_host, (size_t)n * 4, cudaMemcpyHostToDevice));
-  MCB_CUDA(mcb::launch_test_div(n, da, db, dout, nullptr));
-  MCB_CUDA(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  cudaFree(da);
-  cudaFree(db);
-  cudaFree(dout);
+  DevScratch<float> da, db, dout;
+  MCB_CUDA(da.alloc((size_t)n));
+  MCB_CUDA(db.alloc((size_t)n));
+  MCB_CUDA(dout.alloc((size_t)n));
+  MCB_CUDA(cudaMemcpy(da.p, a_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(cudaMemcpy(db.p, mu_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_div(n, da.p, db.p, dout.p, nullptr));
+  MCB_CUDA(cudaMemcpy(out_host, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return MCB200_OK;
 }
 
@@ -1003,17 +1018,15 @@ int mcb200_test_accumulate(int device, const float *in_host, int64_t n, uint32_t
     return fail(MCB200_ERR_INVALID, "test_accumulate: bad argument");
   DeviceGuard g(device);
   if (!g.ok) return fail(MCB200_ERR_CUDA, "test_accumulate: cudaSetDevice failed");
-  float *din = nullptr;
-  unsigned *dacc = nullptr;
-  MCB_CUDA(cudaMalloc(&din, (size_t)(n > 0 ? n : 1) * 4));
-  MCB_CUDA(cudaMalloc(&dacc, (mcb::kAccDigits + 1) * sizeof(unsigned)));
-  MCB_CUDA(cudaMemset(dacc, 0, (mcb::kAccDigits + 1) * sizeof(unsigned)));
-  if (n > 0) MCB_CUDA(cudaMemcpy(din, in_host, (size_t)n * 4, cudaMemcpyHostToDevice));
-  MCB_CUDA(mcb::launch_test_accumulate(n, din, dacc, nullptr));
+  DevScratch<float> din;
+  DevScratch<unsigned> dacc;
+  MCB_CUDA(din.alloc((size_t)(n > 0 ? n : 1)));
+  MCB_CUDA(dacc.alloc(mcb::kAccDigits + 1));
+  MCB_CUDA(cudaMemset(dacc.p, 0, (mcb::kAccDigits + 1) * sizeof(unsigned)));
+  if (n > 0) MCB_CUDA(cudaMemcpy(din.p, in_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_accumulate(n, din.p, dacc.p, nullptr));
   unsigned h[mcb::kAccDigits + 1];
-  MCB_CUDA(cudaMemcpy(h, dacc, sizeof h, cudaMemcpyDeviceToHost));
-  cudaFree(din);
-  cudaFree(dacc);
+  MCB_CUDA(cudaMemcpy(h, dacc.p, sizeof h, cudaMemcpyDeviceToHost));
   for (int j = 0; j < mcb::kAccDigits; ++j) out4[j] = h[j];
   if (out_f64) *out_f64 = acc_to_double(h);
   if (h[mcb::kAccDigits]) return fail(MCB200_ERR_RANGE, "test_accumulate: value outside (-2^7, 2^7)");
@@ -1026,20 +1039,17 @@ int mcb200_test_birth(int device, float x_ini, float wmc, float dx, int64_t n, u
   if (n == 0) return MCB200_OK;
   DeviceGuard g(device);
   if (!g.ok) return fail(MCB200_ERR_CUDA, "test_birth: cudaSetDevice failed");
-  unsigned long long *ds = nullptr;
-  float4 *dst = nullptr;
-  void *daos = nullptr;
-  MCB_CUDA(cudaMalloc(&ds, (size_t)n * 8));
-  MCB_CUDA(cudaMalloc(&dst, (size_t)n * 16));
-  MCB_CUDA(cudaMalloc(&daos, (size_t)n * 24));
+  DevScratch<unsigned long long> ds;
+  DevScratch<float4> dst;
+  DevScratch<mcb200_particle> daos;
+  MCB_CUDA(ds.alloc((size_t)n));
+  MCB_CUDA(dst.alloc((size_t)n));
+  MCB_CUDA(daos.alloc((size_t)n));
   const mcb::JumpTable jt = mcb::make_jump_table(mcb::kSeedG, mcb::kSeedC);
   const float cell = x_ini / dx;
-  MCB_CUDA(mcb::launch_birth(n, seed, jt, x_ini, wmc, (int)cell, ds, dst, nullptr));
-  MCB_CUDA(mcb::launch_soa_to_aos(n, ds, dst, daos, nullptr));
-  MCB_CUDA(cudaMemcpy(out_host, daos, (size_t)n * 24, cudaMemcpyDeviceToHost));
-  cudaFree(ds);
-  cudaFree(dst);
-  cudaFree(daos);
+  MCB_CUDA(mcb::launch_birth(n, seed, jt, x_ini, wmc, (int)cell, ds.p, dst.p, nullptr));
+  MCB_CUDA(mcb::launch_soa_to_aos(n, ds.p, dst.p, daos.p, nullptr));
+  MCB_CUDA(cudaMemcpy(out_host, daos.p, (size_t)n * 24, cudaMemcpyDeviceToHost));
   return MCB200_OK;
 }
 
