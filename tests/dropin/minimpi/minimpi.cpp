@@ -234,6 +234,9 @@ bool match(int ctx, int src, int tag, bool take, void *buf, size_t cap, MPI_Stat
           if (!o->consumed) break;
           b.head += o->total;
         }
+        // an empty ring restarts at offset 0, so a quiet exchange keeps touching the same few
+        // pages of the (sparse) shared-memory file instead of walking through all of it
+        if (b.head == b.tail) b.head = b.tail = 0;
       }
       found = true;
       break;
@@ -317,7 +320,7 @@ int MPI_Init(int *, char ***) {
     if (g_size < 1 || g_rank < 0 || g_rank >= g_size) die("bad rank/size %s/%s", r, s);
   }
   const char *e;
-  size_t arena_mb = (e = getenv("MINIMPI_ARENA_MB")) ? (size_t)atol(e) : 256;
+  size_t arena_mb = (e = getenv("MINIMPI_ARENA_MB")) ? (size_t)atol(e) : 64;
   size_t heap_mb = (e = getenv("MINIMPI_HEAP_MB")) ? (size_t)atol(e) : 256;
   if ((e = getenv("MINIMPI_TIMEOUT_S"))) g_timeout_s = atof(e);
   g_arena_bytes = arena_mb << 20;
