@@ -94,6 +94,20 @@ def test_multi_rank_program_against_the_oracle_chain(tmp_path, n, mode):
     assert abs(got.astype(np.float64).sum() - exact.sum()) <= 1e-6 * exact.sum()
 
 
+@pytest.mark.parametrize("name", ["comm", "state_comm", "async_serialization", "rma_serialization"])
+def test_reference_mpi_ctests_with_our_particle(tmp_path, name):
+    """TestComm / TestStateComm / TestAsyncSerialization / TestRmaSerialization
+    (CMakeLists.txt:324-333: `mpirun -n 2`), compiled from the reference's sources with THIS
+    repository's `Particle` (include/mcb200/compat/particle.hpp): the 24-byte record survives the
+    reference's AsyncComm / RmaComm byte for byte (its FNV hash check), and minimpi behaves like
+    the MPI those tests were written for."""
+    exe = os.path.join(HERE, "dropin", "_bin", f"ref_test_{name}")
+    if not os.path.isfile(exe):
+        pytest.skip(f"ref_test_{name} not built (needs /root/reference at build time)")
+    status, _ = launch(2, [exe], timeout=120, cwd=str(tmp_path), capture=True)
+    assert status == 0
+
+
 def test_golden_weights_of_the_program_are_committed():
     """tests/golden/ref_main_weights.npz (make_golden_main.py): what the GPU build of the same
     program is compared with on the box, where the reference does not exist."""
