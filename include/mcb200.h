@@ -30,7 +30,8 @@ enum {
   MCB200_ERR_CUDA = -2,     /* CUDA runtime error (message has the string) */
   MCB200_ERR_NOMEM = -3,    /* host or device allocation failed */
   MCB200_ERR_CAPACITY = -4, /* caller buffer too small */
-  MCB200_ERR_RANGE = -5     /* a weight / deposit outside (-2^7, 2^7): not a Monte-Carlo weight */
+  MCB200_ERR_RANGE = -5,    /* a weight / deposit outside (-2^7, 2^7): not a Monte-Carlo weight */
+  MCB200_ERR_TIMEOUT = -6   /* a multi-GPU run made no progress (a peer died?) and was stopped */
 };
 
 /* include/types/particle.hpp:7-18 -- the 24-byte POD the workers ship over
@@ -192,6 +193,112 @@ int mcb200_layer_set_exchange_parity(mcb200_layer *l, int32_t parity);
  * the bank and reset that slot; *n_out = particles received */
 int mcb200_layer_ingest_inbox(mcb200_layer *l, int32_t from_side, int32_t parity,
                               int64_t *n_out);
+
+
+/* ---- the world: one whole run on N GPUs, driven from C ------------------------------ */
+/* Stands in for Worker::spin (src/worker_sync.cpp:24-135, src/worker_async.cpp:19-105,
+ * src/worker_rma.cpp:15-68) and Worker::gather_weights_absorbed (src/worker.cpp:183-216).
+ * One `mcb200_world` = one rank = one contiguous sub-slab on one GPU (decompose_domain,
+ * src/layer.cpp:17-42, but with the ONE global dx and slices of the ONE global
+ * cross-section table, so that K ranks reproduce the single-rank result bit for bit).
+ * A run is ONE resident kernel per rank: escapees go straight into the neighbour GPU's
+ * memory (peer-mapped rings, the MPI_Put of src/rma_comm.cpp:133-186), source particles
+ * are born in the kernel (src/layer.cpp:101-120), and the run ends when a device-side
+ * global count of disabled histories reaches nb_particles (StateComm,
+ * src/state_comm.cpp:35-65; MPI_Allreduce, src/worker_sync.cpp:112-120).  The host only
+ * launches and waits.  A sub-slab too wide for a CTA-private tally is cut into windows
+ * served by groups of CTAs of the same launch, exchanging through the same rings.
+ *
+ * Ranks in ONE process (one host thread drives N GPUs):
+ *   create x N; connect_local(all pairs); mcb200_world_run(worlds, N, ...)
+ * Ranks in N processes (one per GPU, e.g. under torchrun / mpirun):
+ *   create; export -> ship handle + geom to the other ranks (any transport) -> connect_peer;
+ *   per run: prepare; <barrier across ranks>; launch; wait                                   */
+typedef struct mcb200_world mcb200_world;
+
+typedef struct mcb200_world_desc {
+  int32_t abi_version;       /* MCB200_ABI_VERSION */
+  int32_t device;            /* CUDA device ordinal of this rank */
+  int32_t rank, world_size;
+  float x_min, x_max, x_ini; /* config.yaml keys (src/worker.cpp:315-333) */
+  int32_t nb_cells;
+  float particle_min_weight;
+  const int32_t *cuts;       /* world_size + 1 ascending cell boundaries, cuts[0] = 0,
+                                cuts[world_size] = nb_cells; NULL = the reference's equal
+                                split (src/layer.cpp:24-27).  Results do not depend on them. */
+  const float *sigs;              /* GLOBAL tables, nb_cells entries; NULL = src/layer.cpp:53-63 */
+  const float *absorption_rates;
+  int32_t windows;           /* windows per rank; 0 = as few as fit shared memory */
+  int32_t block;             /* threads per CTA; 0 = auto */
+  int32_t max_ctas;          /* cap on the CTAs of the launch; 0 = fill the GPU */
+  int32_t ring_cap;          /* records per ring (power of two >= 32); 0 = auto */
+  int32_t retire_batch;      /* see mcb200_layer_set_option; 0 = auto */
+  int32_t reserved;
+  int64_t bank_cap;          /* records of a window's overflow bank (power of two); 0 = auto */
+  int64_t inflight_limit;    /* source births pause above this many live histories; 0 = auto */
+} mcb200_world_desc;
+
+/* what a peer must know about a rank's exchange block to store into it */
+typedef struct mcb200_world_geom {
+  int32_t rank, world_size;
+  int32_t stripes;           /* rings per link = warps serving one window */
+  int32_t ring_cap;
+  int64_t block_bytes;
+  int64_t off_rec[2];        /* rings filled by the left [0] / right [1] neighbour */
+  int64_t off_wr_pub[2];     /* their write counts */
+  int64_t off_credit[2];     /* credits for this rank's own sends to the left / right */
+} mcb200_world_geom;
+
+/* one rank's share of a run (counters are for THIS run; the tally is cumulative) */
+typedef struct mcb200_world_result {
+  int64_t events, scatters;        /* particle_step executions / scatter branches on this rank */
+  int64_t n_left, n_right, n_dead; /* histories disabled here: absorbed at the GLOBAL left /
+                                      right border (src/layer.cpp:350-360), below min weight */
+  int64_t births;                  /* source histories born here */
+  int64_t sent_left, sent_right;   /* records shipped to the neighbour ranks (NVLink) */
+  int64_t window_crossings;        /* records exchanged between windows inside this rank */
+  int64_t idle_polls, blocked_passes, bank_pushes, bank_pops;   /* exchange diagnostics */
+  int64_t busy_warp_iterations;    /* event-loop iterations of all warps (load measure) */
+  double w_left, w_right, w_dead;  /* cumulative weight absorbed at the borders / by the dead */
+  double kernel_ms;                /* device time of the resident kernel (CUDA events) */
+  int32_t windows, ctas, block, stripes, ring_cap;
+  int32_t error;                   /* MCB200_OK or the MCB200_ERR_* the kernel raised */
+} mcb200_world_result;
+
+int mcb200_world_create(const mcb200_world_desc *desc, mcb200_world **out);
+void mcb200_world_destroy(mcb200_world *w);
+/* the IPC handle + geometry of this rank's exchange block, for ranks in other processes */
+int mcb200_world_export(mcb200_world *w, uint8_t handle_out[MCB200_IPC_HANDLE_BYTES],
+                        mcb200_world_geom *geom_out);
+/* map another rank's exchange block: every rank connects to every other rank (neighbours for
+ * the rings, the home rank -- the one holding x_ini -- for the global count and `done`) */
+int mcb200_world_connect_peer(mcb200_world *w, int32_t peer_rank,
+                              const uint8_t handle[MCB200_IPC_HANDLE_BYTES],
+                              const mcb200_world_geom *geom);
+int mcb200_world_connect_local(mcb200_world *w, mcb200_world *peer);
+int mcb200_world_disconnect(mcb200_world *w);
+/* a run of nb_particles source histories (seed chain from `seed`, src/layer.cpp:36):
+ * prepare on EVERY rank, then a barrier across ranks, then launch, then wait. */
+int mcb200_world_prepare(mcb200_world *w, int64_t nb_particles, uint64_t seed);
+int mcb200_world_launch(mcb200_world *w);
+int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out);
+/* all ranks live in this process: prepare / launch / wait for each (results may be NULL) */
+int mcb200_world_run(mcb200_world *const *worlds, int32_t n, int64_t nb_particles,
+                     uint64_t seed, mcb200_world_result *results);
+/* this rank's cells [*lo, *lo + *m) */
+int mcb200_world_cells(mcb200_world *w, int32_t *lo, int32_t *m);
+/* this rank's slice of weights_absorbed (m entries; see mcb200_layer_weights_absorbed*) */
+int mcb200_world_tally(mcb200_world *w, float *out_m);
+int mcb200_world_tally_f64(mcb200_world *w, double *out_m);
+int mcb200_world_tally_exact(mcb200_world *w, uint32_t *out_4m, int32_t *lsb_log2);
+int mcb200_world_reset_tally(mcb200_world *w);
+/* Worker::gather_weights_absorbed (src/worker.cpp:183-216) for ranks of one process: the
+ * disjoint slices concatenated, nb_cells entries */
+int mcb200_world_gather_tally_f64(mcb200_world *const *worlds, int32_t n, double *out_nb_cells);
+/* knobs: "max_run_ms" (device-side cap on a run, 0 = none), "stall_ms" (the host stops a run
+ * whose global counters have not moved for this long; default 15000) */
+int mcb200_world_set_option(mcb200_world *w, const char *key, int64_t value);
+void *mcb200_world_stream(mcb200_world *w);
 
 /* weights_absorbed (layer.hpp:92), m entries.  The device keeps every cell as
  * an EXACT 128-bit fixed-point sum of the per-event float deposits (order-,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MCB200_LIB") or os.path.join(HERE, "libmcb200.so")
 
 ABI_VERSION = 1
-OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_RANGE = 0, -1, -2, -3, -4, -5
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_RANGE, ERR_TIMEOUT = 0, -1, -2, -3, -4, -5, -6
 
 # include/types/particle.hpp:7-18 -- 24-byte wire format
 PARTICLE_DTYPE = np.dtype(
@@ -65,6 +65,46 @@ class InboxGeom(C.Structure):
     ]
 
 
+class WorldDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("rank", C.c_int32), ("world_size", C.c_int32),
+        ("x_min", C.c_float), ("x_max", C.c_float), ("x_ini", C.c_float),
+        ("nb_cells", C.c_int32), ("particle_min_weight", C.c_float),
+        ("cuts", C.c_void_p), ("sigs", C.c_void_p), ("absorption_rates", C.c_void_p),
+        ("windows", C.c_int32), ("block", C.c_int32), ("max_ctas", C.c_int32),
+        ("ring_cap", C.c_int32), ("retire_batch", C.c_int32), ("reserved", C.c_int32),
+        ("bank_cap", C.c_int64), ("inflight_limit", C.c_int64),
+    ]
+
+
+class WorldGeom(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32), ("world_size", C.c_int32), ("stripes", C.c_int32),
+        ("ring_cap", C.c_int32), ("block_bytes", C.c_int64),
+        ("off_rec", C.c_int64 * 2), ("off_wr_pub", C.c_int64 * 2), ("off_credit", C.c_int64 * 2),
+    ]
+
+
+class WorldResult(C.Structure):
+    _fields_ = [
+        ("events", C.c_int64), ("scatters", C.c_int64),
+        ("n_left", C.c_int64), ("n_right", C.c_int64), ("n_dead", C.c_int64),
+        ("births", C.c_int64), ("sent_left", C.c_int64), ("sent_right", C.c_int64),
+        ("window_crossings", C.c_int64),
+        ("idle_polls", C.c_int64), ("blocked_passes", C.c_int64),
+        ("bank_pushes", C.c_int64), ("bank_pops", C.c_int64),
+        ("busy_warp_iterations", C.c_int64),
+        ("w_left", C.c_double), ("w_right", C.c_double), ("w_dead", C.c_double),
+        ("kernel_ms", C.c_double),
+        ("windows", C.c_int32), ("ctas", C.c_int32), ("block", C.c_int32),
+        ("stripes", C.c_int32), ("ring_cap", C.c_int32), ("error", C.c_int32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 # every symbol include/mcb200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -91,6 +131,24 @@ SYMBOLS = {
     "mcb200_layer_disconnect_peers": (C.c_int, [_P]),
     "mcb200_layer_set_exchange_parity": (C.c_int, [_P, _I32]),
     "mcb200_layer_ingest_inbox": (C.c_int, [_P, _I32, _I32, C.POINTER(_I64)]),
+    "mcb200_world_create": (C.c_int, [C.POINTER(WorldDesc), C.POINTER(_P)]),
+    "mcb200_world_destroy": (None, [_P]),
+    "mcb200_world_export": (C.c_int, [_P, _P, C.POINTER(WorldGeom)]),
+    "mcb200_world_connect_peer": (C.c_int, [_P, _I32, _P, C.POINTER(WorldGeom)]),
+    "mcb200_world_connect_local": (C.c_int, [_P, _P]),
+    "mcb200_world_disconnect": (C.c_int, [_P]),
+    "mcb200_world_prepare": (C.c_int, [_P, _I64, C.c_uint64]),
+    "mcb200_world_launch": (C.c_int, [_P]),
+    "mcb200_world_wait": (C.c_int, [_P, C.POINTER(WorldResult)]),
+    "mcb200_world_run": (C.c_int, [C.POINTER(_P), _I32, _I64, C.c_uint64, C.POINTER(WorldResult)]),
+    "mcb200_world_cells": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
+    "mcb200_world_tally": (C.c_int, [_P, _P]),
+    "mcb200_world_tally_f64": (C.c_int, [_P, _P]),
+    "mcb200_world_tally_exact": (C.c_int, [_P, _P, C.POINTER(_I32)]),
+    "mcb200_world_reset_tally": (C.c_int, [_P]),
+    "mcb200_world_gather_tally_f64": (C.c_int, [C.POINTER(_P), _I32, _P]),
+    "mcb200_world_set_option": (C.c_int, [_P, C.c_char_p, _I64]),
+    "mcb200_world_stream": (_P, [_P]),
     "mcb200_layer_weights_absorbed": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_f64": (C.c_int, [_P, _P]),
     "mcb200_layer_weights_absorbed_exact": (C.c_int, [_P, _P, C.POINTER(_I32)]),

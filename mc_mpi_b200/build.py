@@ -17,8 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmcb200.so")
 
-CUDA_SOURCES = ["mcb_kernels.cu", "mcb_layer.cu", "mcb_facade.cu"]
-HEADERS = ["mcb_math.cuh", "mcb_kernels.cuh", os.path.join(INCLUDE, "mcb200.h"),
+CUDA_SOURCES = ["mcb_kernels.cu", "mcb_world_kernel.cu", "mcb_layer.cu", "mcb_world.cu", "mcb_facade.cu"]
+HEADERS = ["mcb_math.cuh", "mcb_kernels.cuh", "mcb_event.cuh", "mcb_world.cuh", "mcb_host.hpp", os.path.join(INCLUDE, "mcb200.h"),
            os.path.join(INCLUDE, "mcb200", "layer.hpp"),
            os.path.join(INCLUDE, "mcb200", "culayer.hpp")]
 

@@ -17,183 +17,9 @@
 //      into contiguous left / right send buffers by gather_stripes_kernel.
 // Nothing on this path is a contraction: no tensor cores by design.
 #include "mcb_kernels.cuh"
+#include "mcb_event.cuh"
 
 namespace mcb {
-
-#define MCB_FULL 0xffffffffu
-
-// ---------------------------------------------------------------- helpers --
-
-// ---- the CTA-PRIVATE accumulator: four 32-bit digits in shared memory ---------------------
-// Exact deposit of one float into a 128-bit accumulator (see mcb_kernels.cuh): the 24-bit
-// significand goes to bit position (exponent - 30) of a little-endian number held in four
-// 32-bit digits `w[0], w[stride], w[2*stride], w[3*stride]`.  Common case (acc_add_smem
-// below): one native ATOMS.ADD when the significand sits inside one digit, two when it
-// straddles; carries ripple by further adds only when a digit wraps.  The final digits do
-// not depend on the interleaving: every step is an exact add modulo 2^128.
-
-// general case: zeros, deposits below 2^-97, negative deposits, out-of-range values
-__device__ __noinline__ void acc_add_slow(unsigned *w, int stride, float v, unsigned *range_flag) {
-  const unsigned b = __float_as_uint(v);
-  const unsigned e = (b >> 23) & 0xffu;
-  unsigned mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
-  int pos = (int)(e ? e : 1u) - (150 + kAccLsbLog2);   // bit position of the significand's LSB
-  if (pos < 0) {                                        // below 2^-97: drop the bits under the LSB
-    mant = pos > -24 ? mant >> (-pos) : 0u;
-    pos = 0;
-  }
-  if (mant == 0u) return;
-  if (pos > 32 * kAccDigits - 25) {                     // |v| >= 2^8 (or inf / nan): not a weight
-    atomicExch(range_flag, 1u);
-    return;
-  }
-  int j = pos >> 5;
-  const int o = pos & 31;
-  const unsigned lo = mant << o;
-  const unsigned hi = __funnelshift_l(mant, 0u, o);     // bits pushed into the next digit
-  if ((int)b >= 0) {
-    unsigned old = atomicAdd(&w[j * stride], lo);
-    unsigned c = hi + (old > ~lo ? 1u : 0u);
-    while (c != 0u && ++j < kAccDigits) {
-      old = atomicAdd(&w[j * stride], c);
-      c = old > ~c ? 1u : 0u;
-    }
-  } else {                                              // negative deposit: exact subtract
-    unsigned old = atomicSub(&w[j * stride], lo);
-    unsigned c = hi + (old < lo ? 1u : 0u);
-    while (c != 0u && ++j < kAccDigits) {
-      old = atomicSub(&w[j * stride], c);
-      c = old < c ? 1u : 0u;
-    }
-  }
-}
-
-// a carry out of digit j-1 rippling upwards (a digit wraps once in 2^32 units: rare)
-__device__ __noinline__ void acc_ripple(unsigned *w, int stride, int j) {
-  for (; j < kAccDigits; ++j)
-    if (atomicAdd(&w[j * stride], 1u) != 0xffffffffu) break;
-}
-
-// ---- the GLOBAL accumulator: the same 128-bit number as two 64-bit digits ---------------
-// In global memory the accumulator of cell c is g[c] (bits 0..63) and g[ncell + c] (bits
-// 64..127): sm_100a has native 64-bit global atomics, and a weight-sized deposit (>= 2^-56)
-// lands entirely in the upper digit, so the common case is ONE fire-and-forget RED.E.ADD.64
-// with no return value to wait for.  Used per event when the CTA-private copy does not fit
-// shared memory (tally_mode 2), and once per CTA by the flush of the private copies.
-
-// exact signed add of |v| = mag * 2^-120 (mag < 2^128 given as two 64-bit halves)
-__device__ __forceinline__ void gacc_add128(unsigned long long *g, int ncell,
-                                            unsigned long long lo, unsigned long long hi,
-                                            bool negative) {
-  if (!negative) {
-    if (lo) {
-      const unsigned long long old = atomicAdd(&g[0], lo);
-      hi += old > ~lo ? 1ull : 0ull;
-    }
-    if (hi) atomicAdd(&g[ncell], hi);
-  } else {  // subtract: add the two's complement
-    const unsigned long long nlo = ~lo + 1ull;
-    unsigned long long nhi = ~hi + (lo == 0ull ? 1ull : 0ull);
-    if (nlo) {
-      const unsigned long long old = atomicAdd(&g[0], nlo);
-      nhi += old > ~nlo ? 1ull : 0ull;
-    }
-    if (nhi) atomicAdd(&g[ncell], nhi);
-  }
-}
-
-__device__ __noinline__ void gacc_add_slow(unsigned long long *g, int ncell, float v,
-                                           unsigned *range_flag) {
-  const unsigned b = __float_as_uint(v);
-  const unsigned e = (b >> 23) & 0xffu;
-  unsigned mant = (b & 0x7fffffu) | (e ? 0x800000u : 0u);
-  int pos = (int)(e ? e : 1u) - (150 + kAccLsbLog2);
-  if (pos < 0) {
-    mant = pos > -24 ? mant >> (-pos) : 0u;
-    pos = 0;
-  }
-  if (mant == 0u) return;
-  if (pos > 32 * kAccDigits - 25) {
-    atomicExch(range_flag, 1u);
-    return;
-  }
-  unsigned long long lo, hi;
-  if (pos >= 64) {
-    lo = 0ull;
-    hi = (unsigned long long)mant << (pos - 64);
-  } else {
-    lo = (unsigned long long)mant << pos;
-    hi = pos > 40 ? (unsigned long long)mant >> (64 - pos) : 0ull;
-  }
-  gacc_add128(g, ncell, lo, hi, (int)b < 0);
-}
-
-// the hot global deposit: v positive, normal, in [2^-97, 2^7)
-__device__ __forceinline__ void gacc_add(unsigned long long *g, int ncell, float v,
-                                         unsigned *range_flag) {
-  const unsigned b = __float_as_uint(v);
-  const unsigned pos = (b >> 23) - (unsigned)(150 + kAccLsbLog2);  // exponent (and sign) - 30
-  if (pos - 64u <= (unsigned)(32 * kAccDigits - 25 - 64)) {
-    // [2^-56, 2^7): entirely inside the upper digit -> one RED, nothing to wait for
-    const unsigned long long mant = (unsigned long long)((b & 0x7fffffu) | 0x800000u);
-    atomicAdd(&g[ncell], mant << (pos - 64u));
-  } else {
-    gacc_add_slow(g, ncell, v, range_flag);
-  }
-}
-
-// add a CTA-private accumulator (four 32-bit digits) into the global one
-__device__ __forceinline__ void gacc_merge(unsigned long long *g, int ncell,
-                                           const unsigned d[kAccDigits]) {
-  gacc_add128(g, ncell, (unsigned long long)d[0] | ((unsigned long long)d[1] << 32),
-              (unsigned long long)d[2] | ((unsigned long long)d[3] << 32), false);
-}
-
-// The same deposit into a CTA-private accumulator in SHARED memory, addressed by its
-// 32-bit shared-window byte address (`w` = digit 0 of the cell, `stride` bytes between
-// digits) with explicit atom.shared -- see mcb_math.cuh on why not generic pointers.
-__device__ __forceinline__ void acc_add_smem(unsigned w, unsigned stride, float v,
-                                             unsigned *range_flag) {
-  const unsigned b = __float_as_uint(v);
-  const unsigned pos = (b >> 23) - (unsigned)(150 + kAccLsbLog2);
-  if (pos <= (unsigned)(32 * kAccDigits - 25)) {
-    const unsigned mant = (b & 0x7fffffu) | 0x800000u;
-    const unsigned j = pos >> 5;
-    const unsigned o = pos & 31u;
-    const unsigned lo = mant << o;
-    const unsigned hi = __funnelshift_l(mant, 0u, o);
-    const unsigned d = w + j * stride;
-    const unsigned old = atoms_add_u32(d, lo);
-    const unsigned c = hi + (old > ~lo ? 1u : 0u);
-    if (c != 0u && j < (unsigned)(kAccDigits - 1)) {
-      const unsigned old2 = atoms_add_u32(d + stride, c);
-      if (old2 > ~c)
-        acc_ripple(static_cast<unsigned *>(__cvta_shared_to_generic(w)), (int)(stride >> 2),
-                   (int)j + 2);
-    }
-  } else {
-    acc_add_slow(static_cast<unsigned *>(__cvta_shared_to_generic(w)), (int)(stride >> 2), v,
-                 range_flag);
-  }
-}
-
-// a / b in round-to-nearest with the reciprocal hoisted out of the event loop.  div.rn.f32's
-// fast path is  r0 = MUFU.RCP(b); r = r0 + r0*(1 - b*r0); q0 = a*r; q = q0 + r*(a - b*q0)
-// guarded by FCHK (exponent ranges).  `b` (the direction cosine) only changes when a particle
-// scatters, so r is computed then; the per-event part is 3 FFMA.  The guard used here is
-// stricter than FCHK: |b| in (EPS, 2^60) when r is formed, |a| in [2^-100, 2^100) per event;
-// anything else takes __fdiv_rn.
-__device__ __forceinline__ float recip_for_div(float b) {
-  const float ab = fabsf(b);
-  if (!(ab > MCB_EPS && ab < 0x1p60f)) return 0.0f;  // 0 = "no fast path for this divisor"
-  float r0;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
-  return __fmaf_rn(r0, __fmaf_rn(-b, r0, 1.0f), r0);
-}
-__device__ __forceinline__ float div_by_recip(float a, float b, float r) {
-  const float q0 = __fmul_rn(a, r);
-  return __fmaf_rn(r, __fmaf_rn(-b, q0, a), q0);
-}
 
 struct TrackSmem {
   MathTables math;
@@ -352,54 +178,8 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      const int il = idx - lo;                                   // :129
-      const CellXs xs = SHARED ? lds_f32x4(xs_s + (unsigned)il * 16u)
-                               : __ldg(&p.xs[il]);               // :131-133
-      seed = lcg_next(seed);                                     // :136
-      const float h = lcg_to_real(seed);
-
-      const bool neg = mu < 0.0f;                                // :143-152
-      int inew = neg ? idx - 1 : idx + 1;
-      const float xe = __fmul_rn(__int2float_rn(neg ? idx : idx + 1), dx);
-      float de = MCB_MAXREAL;                                    // :154-158
-      {
-        const float a = __fsub_rn(xe, x);
-        const unsigned ea = (__float_as_uint(a) & 0x7fffffffu) - 0x0d800000u;  // 2^-100 ..
-        if (rmu != 0.0f && ea < 0x64000000u) de = div_by_recip(a, mu, rmu);    // .. 2^100
-        else if (mu < -MCB_EPS || MCB_EPS < mu) de = __fdiv_rn(a, mu);
-      }
-
-      // :137 di = -logf(h)/sig_i, :160 `di < di_edge`.  The reference only uses di when the
-      // flight ends inside the cell; when it reaches the edge, di is overwritten (:170).  Since
-      // -ln h >= 1 - h, a flight is CERTAIN to reach the edge when (1 - h)/sig_i exceeds
-      // di_edge by more than all roundings involved: glibc's logf is within 1 ulp, the two
-      // float divisions / products within 2^-24 each, xs.z is 1/sig_i lowered by 2^-20, and
-      // the margin asked for here is 2^-18.  On a thin slab that is 99.9 % of the events, and
-      // they skip the logf and the divide without changing one bit of the result; the others
-      // take the exact path.  (xs.z = +inf for sig_i <= EPS; NaN / inf compare false -> exact.)
-      float di = MCB_MAXREAL;
-      const bool certain_edge =
-          __fmul_rn(__fsub_rn(1.0f, h), xs.z) > __fmul_rn(de, 1.0f + 0x1p-18f);
-      if (!certain_edge && xs.y > MCB_EPS) di = __fdiv_rn(-logf_glibc(h, tb_s), xs.y);
-
-      if (di < de) {                                             // :160-166
-        inew = idx;
-        x = __fadd_rn(x, __fmul_rn(di, mu));
-        seed = lcg_next(seed);
-        mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
-        rmu = recip_for_div(mu);
-        ++n_sc;
-      } else {                                                   // :167-172
-        di = de;
-        x = xe;
-      }
-      const float e = expf_glibc_nonpos(__fmul_rn(-xs.x, di), tb_s);
-      const float dw = __fmul_rn(__fsub_rn(1.0f, e), wmc);       // :175
-      wmc = __fsub_rn(wmc, dw);                                  // :178
-      // :179, exactly
-      if (SHARED) acc_add_smem(acc_s + (unsigned)il * 4u, acc_stride, dw, &p.ctr->acc_range);
-      else gacc_add(&gacc[il], ncell, dw, &p.ctr->acc_range);
-      idx = inew;                                                // :181
+      event_step<SHARED>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
+                         p.xs, gacc, ncell, &p.ctr->acc_range);
       ++n_ev;
     }
   }

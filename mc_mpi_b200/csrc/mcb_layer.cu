@@ -21,36 +21,53 @@
 #include <vector>
 
 #include "../../include/mcb200.h"
+#include "mcb_host.hpp"
 #include "mcb_kernels.cuh"
 
-namespace {
+namespace mcb {
 
-thread_local std::string g_last_error;
+static thread_local std::string g_last_error;
 
 int fail(int code, const std::string &msg) {
   g_last_error = msg;
   return code;
 }
 
-#define MCB_CUDA(expr)                                                                   \
-  do {                                                                                   \
-    cudaError_t e__ = (expr);                                                            \
-    if (e__ != cudaSuccess)                                                              \
-      return fail(e__ == cudaErrorMemoryAllocation ? MCB200_ERR_NOMEM : MCB200_ERR_CUDA, \
-                  std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
-  } while (0)
+CellXs host_cell_xs(float sig, float a) {
+  const float interaction_rate = (float)(1.0 - (double)a);
+  const float sig_a = sig * a;
+  const float sig_i = sig * interaction_rate;
+  // a float safely below 1/sig_i for the kernel's "certain crossing" test
+  const float inv_lb = sig_i > MCB_EPS ? (float)((1.0 / (double)sig_i) * (1.0 - 0x1p-20))
+                                       : std::numeric_limits<float>::infinity();
+  return make_float4(sig_a, sig_i, inv_lb, 0.0f);
+}
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = false;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
+double acc_to_double(const unsigned d[kAccDigits]) {
+  unsigned __int128 u = 0;
+  for (int j = kAccDigits - 1; j >= 0; --j) u = (u << 32) | d[j];
+  return std::ldexp((double)(__int128)u, kAccLsbLog2);
+}
+
+void acc_halves_to_digits(const unsigned *raw, int ncell, int m, unsigned *out) {
+  // 32-bit digit j of cell c is word (j & 1) of half j / 2 (little endian)
+  const size_t nc = (size_t)ncell;
+  for (int c = 0; c < m; ++c)
+    for (int j = 0; j < kAccDigits; ++j)
+      out[(size_t)c * kAccDigits + j] = raw[(size_t)(j / 2) * 2 * nc + 2 * (size_t)c + (size_t)(j & 1)];
+}
+
+const char *last_error_cstr() { return g_last_error.c_str(); }
+void set_last_error(const std::string &m) { g_last_error = m; }
+std::string get_last_error() { return g_last_error; }
+
+}  // namespace mcb
+
+namespace {
+
+using mcb::DeviceGuard;
+using mcb::acc_to_double;
+using mcb::fail;
 
 // scratch device allocation of the known-answer-test entry points: freed on every return path
 template <typename T>
@@ -68,14 +85,6 @@ struct SoaBuf {
   float4 *st = nullptr;
   long long cap = 0;
 };
-
-// 128-bit two's-complement accumulator (4 little-endian 32-bit digits, LSB
-// 2^kAccLsbLog2) -> double, rounded once
-double acc_to_double(const unsigned d[mcb::kAccDigits]) {
-  unsigned __int128 u = 0;
-  for (int j = mcb::kAccDigits - 1; j >= 0; --j) u = (u << 32) | d[j];
-  return std::ldexp((double)(__int128)u, mcb::kAccLsbLog2);
-}
 
 }  // namespace
 
@@ -212,17 +221,8 @@ int stage_reserve(mcb200_layer *l, long long n) {
 // -ffp-contract=off and no -mfma, like the reference: plain IEEE float ops)
 int upload_xs(mcb200_layer *l) {
   std::vector<mcb::CellXs> xs((size_t)l->m);
-  for (int i = 0; i < l->m; ++i) {
-    const float a = l->absorption_rates[(size_t)i];
-    const float interaction_rate = (float)(1.0 - (double)a);
-    const float sig_a = l->sigs[(size_t)i] * a;
-    const float sig_i = l->sigs[(size_t)i] * interaction_rate;
-    // a float safely below 1/sig_i for the kernel's "certain crossing" test
-    const float inv_lb = sig_i > MCB_EPS
-                             ? (float)((1.0 / (double)sig_i) * (1.0 - 0x1p-20))
-                             : std::numeric_limits<float>::infinity();
-    xs[(size_t)i] = make_float4(sig_a, sig_i, inv_lb, 0.0f);
-  }
+  for (int i = 0; i < l->m; ++i)
+    xs[(size_t)i] = mcb::host_cell_xs(l->sigs[(size_t)i], l->absorption_rates[(size_t)i]);
   MCB_CUDA(cudaMemcpyAsync(l->d_xs, xs.data(), xs.size() * sizeof(mcb::CellXs),
                            cudaMemcpyHostToDevice, l->stream));
   MCB_CUDA(cudaStreamSynchronize(l->stream));
@@ -238,13 +238,7 @@ int fetch_tally(mcb200_layer *l, std::vector<unsigned> *out) {
                            cudaMemcpyDeviceToHost, l->stream));
   MCB_CUDA(cudaStreamSynchronize(l->stream));
   out->resize((size_t)l->m * mcb::kAccDigits);
-  const size_t nc = (size_t)l->ncell();
-  // device layout: 64-bit halves [2][ncell]; 32-bit digit j of cell c is word (j & 1) of
-  // half j / 2 (little endian)
-  for (int c = 0; c < l->m; ++c)
-    for (int j = 0; j < mcb::kAccDigits; ++j)
-      (*out)[(size_t)c * mcb::kAccDigits + j] =
-          raw[(size_t)(j / 2) * 2 * nc + 2 * (size_t)c + (size_t)(j & 1)];
+  mcb::acc_halves_to_digits(raw.data(), l->ncell(), l->m, out->data());
   return MCB200_OK;
 }
 
@@ -456,7 +450,7 @@ int push_any(mcb200_layer *l, const void *src, bool src_is_device, long long n) 
 
 extern "C" {
 
-const char *mcb200_last_error(void) { return g_last_error.c_str(); }
+const char *mcb200_last_error(void) { return mcb::last_error_cstr(); }
 int mcb200_abi_version(void) { return MCB200_ABI_VERSION; }
 int mcb200_device_count(void) {
   int n = 0;
@@ -542,9 +536,9 @@ int mcb200_layer_create(const mcb200_layer_desc *d, mcb200_layer **out) {
             "cudaMemset tally");
   if (rc == MCB200_OK) cuda_ok(cudaStreamSynchronize(l->stream), "cudaStreamSynchronize");
   if (rc != MCB200_OK) {
-    std::string keep = g_last_error;
+    std::string keep = mcb::get_last_error();
     mcb200_layer_destroy(l);
-    g_last_error = keep;
+    mcb::set_last_error(keep);
     return rc;
   }
   *out = l;
@@ -602,9 +596,9 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
   if (rc) return rc;
   DeviceGuard g(l->device);
   auto bail = [&](int code) {
-    std::string keep = g_last_error;
+    std::string keep = mcb::get_last_error();
     mcb200_layer_destroy(l);
-    g_last_error = keep;
+    mcb::set_last_error(keep);
     return code;
   };
   cudaStreamSynchronize(src->stream);
