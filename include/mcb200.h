@@ -245,7 +245,6 @@ typedef struct mcb200_world_geom {
   int32_t ring_cap;
   int64_t block_bytes;
   int64_t off_rec[2];        /* rings filled by the left [0] / right [1] neighbour */
-  int64_t off_wr_pub[2];     /* their write counts */
   int64_t off_credit[2];     /* credits for this rank's own sends to the left / right */
 } mcb200_world_geom;
 
@@ -258,7 +257,6 @@ typedef struct mcb200_world_result {
   int64_t sent_left, sent_right;   /* records shipped to the neighbour ranks (NVLink) */
   int64_t window_crossings;        /* records exchanged between windows inside this rank */
   int64_t idle_polls, blocked_passes, bank_pushes, bank_pops;   /* exchange diagnostics */
-  int64_t busy_warp_iterations;    /* event-loop iterations of all warps (load measure) */
   double w_left, w_right, w_dead;  /* cumulative weight absorbed at the borders / by the dead */
   double kernel_ms;                /* device time of the resident kernel (CUDA events) */
   int32_t windows, ctas, block, stripes, ring_cap;

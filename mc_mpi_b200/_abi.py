@@ -82,7 +82,7 @@ class WorldGeom(C.Structure):
     _fields_ = [
         ("rank", C.c_int32), ("world_size", C.c_int32), ("stripes", C.c_int32),
         ("ring_cap", C.c_int32), ("block_bytes", C.c_int64),
-        ("off_rec", C.c_int64 * 2), ("off_wr_pub", C.c_int64 * 2), ("off_credit", C.c_int64 * 2),
+        ("off_rec", C.c_int64 * 2), ("off_credit", C.c_int64 * 2),
     ]
 
 
@@ -94,7 +94,6 @@ class WorldResult(C.Structure):
         ("window_crossings", C.c_int64),
         ("idle_polls", C.c_int64), ("blocked_passes", C.c_int64),
         ("bank_pushes", C.c_int64), ("bank_pops", C.c_int64),
-        ("busy_warp_iterations", C.c_int64),
         ("w_left", C.c_double), ("w_right", C.c_double), ("w_dead", C.c_double),
         ("kernel_ms", C.c_double),
         ("windows", C.c_int32), ("ctas", C.c_int32), ("block", C.c_int32),

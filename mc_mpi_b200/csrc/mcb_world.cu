@@ -89,7 +89,7 @@ unsigned ilog2(unsigned v) {
 }
 
 // layout of the inner-link area of one rank: per inner boundary b (between windows b, b+1)
-// two rings (right-going, left-going), each with its write counts and credits; then the banks
+// two rings (right-going, left-going), each followed by its credit counters; then the banks
 struct InnerLayout {
   size_t ring_bytes, cnt_bytes, link_bytes, bank_rec_bytes, bank_bytes, total;
   size_t banks_off;
@@ -98,7 +98,7 @@ InnerLayout inner_layout(int V, int S, unsigned ring_cap, unsigned bank_cap) {
   InnerLayout q{};
   q.ring_bytes = align256((size_t)S * ring_cap * sizeof(mcb200_particle));
   q.cnt_bytes = align256((size_t)S * sizeof(unsigned));
-  q.link_bytes = 2 * (q.ring_bytes + 2 * q.cnt_bytes);
+  q.link_bytes = 2 * (q.ring_bytes + q.cnt_bytes);
   q.banks_off = (size_t)(V > 1 ? V - 1 : 0) * q.link_bytes;
   q.bank_rec_bytes = align256((size_t)bank_cap * sizeof(mcb200_particle));
   q.bank_bytes = q.bank_rec_bytes + 256;   // + head / tail
@@ -118,14 +118,14 @@ int choose_shape(mcb200_world *w, const mcb200_world_desc *d, int m_max_all) {
       return fail(MCB200_ERR_INVALID, "world: block must be a multiple of 32 in [32, 1024]");
     const int bps = 1024 / block > 0 ? 1024 / block : 1;
     const size_t budget = prop.sharedMemPerMultiprocessor / (size_t)bps - 1024;
-    const size_t fixed = mcb::world_smem_bytes(0);
+    const size_t fixed = mcb::world_smem_bytes(0, block);
     if (budget <= fixed + 64) continue;
     const int mw_max = (int)((budget - fixed) / (sizeof(mcb::CellXs) + mcb::kAccDigits * sizeof(unsigned)));
     int V = d->windows > 0 ? d->windows : (m_max_all + mw_max - 1) / mw_max;
     if (V < 1) V = 1;
     if (V > m_max_all) V = m_max_all;
     const int mw = (m_max_all + V - 1) / V;
-    if (mcb::world_smem_bytes(mw) > prop.sharedMemPerBlockOptin) {
+    if (mcb::world_smem_bytes(mw, block) > prop.sharedMemPerBlockOptin) {
       if (d->block > 0 && d->windows > 0)
         return fail(MCB200_ERR_INVALID, "world: a window does not fit shared memory");
       if (d->block > 0) break;
@@ -185,7 +185,7 @@ int alloc_device(mcb200_world *w) {
   MCB_CUDA(cudaMalloc(&w->d_done_ptrs, (size_t)w->K * sizeof(unsigned *)));
   MCB_CUDA(cudaMallocHost(&w->h_ctr, sizeof(mcb::WorldCounters)));
   MCB_CUDA(cudaMallocHost(&w->h_prog, 2 * sizeof(unsigned long long)));
-  // the exported block: ctrl | rings from left, from right | their write counts | my credits
+  // the exported block: ctrl | rings filled by the left / right neighbour | credits for my sends
   mcb200_world_geom &q = w->geom;
   q.rank = w->rank;
   q.world_size = w->K;
@@ -197,10 +197,6 @@ int alloc_device(mcb200_world *w) {
   for (int s = 0; s < 2; ++s) {
     q.off_rec[s] = (int64_t)off;
     off += ring_bytes;
-  }
-  for (int s = 0; s < 2; ++s) {
-    q.off_wr_pub[s] = (int64_t)off;
-    off += cnt_bytes;
   }
   for (int s = 0; s < 2; ++s) {
     q.off_credit[s] = (int64_t)off;
@@ -245,7 +241,7 @@ int upload_windows(mcb200_world *w) {
                                             std::to_string(k) + ")");
   const InnerLayout il = inner_layout(V, w->S, w->ring_cap, w->bank_cap);
   auto inner_ring = [&](int b, int dir) {   // dir 0 = right-going (b -> b+1), 1 = left-going
-    return w->d_inner + (size_t)b * il.link_bytes + (size_t)dir * (il.ring_bytes + 2 * il.cnt_bytes);
+    return w->d_inner + (size_t)b * il.link_bytes + (size_t)dir * (il.ring_bytes + il.cnt_bytes);
   };
   std::vector<mcb::WindowDesc> tab((size_t)V);
   for (int v = 0; v < V; ++v) {
@@ -266,25 +262,21 @@ int upload_windows(mcb200_world *w) {
         unsigned char *snd = inner_ring(b, s == 1 ? 0 : 1);
         unsigned char *rcv = inner_ring(b, s == 1 ? 1 : 0);
         o.rec = reinterpret_cast<unsigned long long *>(snd);
-        o.wr_pub = reinterpret_cast<unsigned *>(snd + il.ring_bytes);
-        o.credit = reinterpret_cast<const unsigned *>(snd + il.ring_bytes + il.cnt_bytes);
+        o.credit = reinterpret_cast<const unsigned *>(snd + il.ring_bytes);
         o.mode = 1;
         o.outer = 0;
         in.rec = reinterpret_cast<const unsigned long long *>(rcv);
-        in.wr_pub = reinterpret_cast<const unsigned *>(rcv + il.ring_bytes);
-        in.credit = reinterpret_cast<unsigned *>(rcv + il.ring_bytes + il.cnt_bytes);
+        in.credit = reinterpret_cast<unsigned *>(rcv + il.ring_bytes);
         in.present = 1;
       } else if (nr >= 0 && nr < K) {
         // the neighbour rank's exchange block: I store into ITS "from side 1-s" ring, it
         // stores into MY "from side s" ring; credits live with the producer
         const mcb200_world::Peer &pr = w->peers[(size_t)nr];
         o.rec = reinterpret_cast<unsigned long long *>(pr.base + pr.geom.off_rec[1 - s]);
-        o.wr_pub = reinterpret_cast<unsigned *>(pr.base + pr.geom.off_wr_pub[1 - s]);
         o.credit = reinterpret_cast<const unsigned *>(w->d_xblock + w->geom.off_credit[s]);
         o.mode = 1;
         o.outer = 1;
         in.rec = reinterpret_cast<const unsigned long long *>(w->d_xblock + w->geom.off_rec[s]);
-        in.wr_pub = reinterpret_cast<const unsigned *>(w->d_xblock + w->geom.off_wr_pub[s]);
         in.credit = reinterpret_cast<unsigned *>(pr.base + pr.geom.off_credit[1 - s]);
         in.present = 1;
       } else {
@@ -427,7 +419,7 @@ int mcb200_world_create(const mcb200_world_desc *d, mcb200_world **out) {
     int mw = 0;
     for (int v = 0; v < w->V; ++v)
       if (w->win_lo[(size_t)v + 1] - w->win_lo[(size_t)v] > mw) mw = w->win_lo[(size_t)v + 1] - w->win_lo[(size_t)v];
-    if (mcb::world_smem_bytes(mw) > w->cfg.smem)
+    if (mcb::world_smem_bytes(mw, w->cfg.block) > w->cfg.smem)
       return bail(fail(MCB200_ERR_INVALID, "world_create: internal: window larger than planned"));
   }
   // rings: ~2M records per link in total, per-stripe capacity a power of two in [64, 1024]
@@ -559,17 +551,12 @@ int mcb200_world_prepare(mcb200_world *w, int64_t nb_particles, uint64_t seed) {
     int rc = upload_windows(w);
     if (rc) return rc;
   }
-  // every counter of the exchange starts a run at zero (the rings are empty between runs);
-  // all ranks do this BEFORE the barrier that precedes the launches
-  MCB_CUDA(cudaMemsetAsync(w->d_xblock, 0, sizeof(mcb::WorldCtrl), w->stream));
-  const size_t cnt_bytes = (size_t)(w->geom.block_bytes - w->geom.off_wr_pub[0]);
-  MCB_CUDA(cudaMemsetAsync(w->d_xblock + w->geom.off_wr_pub[0], 0, cnt_bytes, w->stream));
+  // A run starts with zeroed rings and credits (a slot's lap parity is only meaningful
+  // from a zeroed ring, and the kernels count from zero); the rings are empty between runs,
+  // so nothing is lost.  All ranks do this BEFORE the barrier that precedes the launches.
+  MCB_CUDA(cudaMemsetAsync(w->d_xblock, 0, (size_t)w->geom.block_bytes, w->stream));
   const InnerLayout il = inner_layout(w->V, w->S, w->ring_cap, w->bank_cap);
-  for (int b = 0; b + 1 < w->V; ++b)
-    for (int dir = 0; dir < 2; ++dir)
-      MCB_CUDA(cudaMemsetAsync(w->d_inner + (size_t)b * il.link_bytes +
-                                   (size_t)dir * (il.ring_bytes + 2 * il.cnt_bytes) + il.ring_bytes,
-                               0, 2 * il.cnt_bytes, w->stream));
+  if (il.banks_off > 0) MCB_CUDA(cudaMemsetAsync(w->d_inner, 0, il.banks_off, w->stream));
   // banks: head == tail between runs and the lap parity of every slot is consistent with
   // them, so they carry over; after a failed run everything is wiped
   if (w->bank_dirty) {
@@ -597,6 +584,7 @@ int mcb200_world_launch(mcb200_world *w) {
   p.minw = w->minw;
   p.retire_batch = w->retire_batch;
   p.ring_cap = w->ring_cap;
+  p.ring_log2 = ilog2(w->ring_cap);
   const bool is_home = w->rank == w->home_rank;
   p.src_window = -1;
   if (is_home && w->src_cell >= 0)
@@ -699,7 +687,6 @@ int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out) {
     out->blocked_passes = (int64_t)c.blocked_passes;
     out->bank_pushes = (int64_t)c.bank_pushes;
     out->bank_pops = (int64_t)c.bank_pops;
-    out->busy_warp_iterations = (int64_t)c.busy_iters;
     double wc[3] = {0, 0, 0};
     int rc = fetch_world_tally(w, nullptr, wc);
     if (rc) return rc;

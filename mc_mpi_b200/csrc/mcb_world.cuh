@@ -8,13 +8,15 @@
 //     (V = 1 when the CTA-private tally of the whole sub-slab fits shared memory);
 //   * every directed link window -> neighbouring window is a set of single-producer /
 //     single-consumer RINGS, one per warp ("stripe"): warp w of the producing window stores
-//     its escapees as 24-byte wire records into stripe w of the consuming window's memory and
-//     publishes its write count with a release store; warp w of the consuming window polls
-//     that count in its OWN memory, takes the records into idle lanes and returns credits.
+//     its escapees as 24-byte wire records into stripe w of the consuming window's memory;
+//     warp w of the consuming window polls the next slots of that stripe in its OWN memory,
+//     takes the records that have arrived into idle lanes and returns credits.  Every 8-byte
+//     word of a slot carries the slot's lap parity in a bit the record never uses, so a word
+//     validates itself: no fence, no published count, no atomics on the path, no host.
 //     Between the last window of rank r and the first window of rank r+1 the consumer's
 //     memory is peer-mapped over NVLink: the escapee stores ARE the communication, exactly
 //     RmaComm's MPI_Put into the neighbour's window (src/rma_comm.cpp:133-186) with the
-//     occupancy word replaced by two monotone counters.  No atomics on the path, no host;
+//     occupancy word replaced by per-slot parity + a credit counter;
 //   * a ring that is full blocks the sending lanes (back-pressure); a warp with blocked lanes
 //     drains its own inbound stripes into the window's BANK (a multi-producer /
 //     multi-consumer queue in local memory) so that two neighbours can never wait on each
@@ -36,7 +38,6 @@ constexpr int kWorldMaxWarps = 32;   // warps per CTA
 // what a window PRODUCES into (side 0 = towards lower cells, 1 = towards higher cells)
 struct LinkOut {
   unsigned long long *rec;   // consumer's ring memory [stripes][cap][3 words]
-  unsigned *wr_pub;          // consumer's copy of this link's write counts [stripes]
   const unsigned *credit;    // LOCAL: records the consumer has taken [stripes] (it stores them)
   int mode;                  // 0 = global border: absorb (src/layer.cpp:350-360); 1 = ring
   int outer;                 // 1 = the link leaves the rank (statistics only)
@@ -44,14 +45,13 @@ struct LinkOut {
 // what a window CONSUMES from (side 0 = from the lower neighbour, 1 = from the higher one)
 struct LinkIn {
   const unsigned long long *rec;  // LOCAL ring memory [stripes][cap][3 words]
-  const unsigned *wr_pub;         // LOCAL write counts [stripes] (the producer stores them)
   unsigned *credit;               // producer's credit array [stripes]
   int present;
   int pad;
 };
 // the window's bank: records waiting for a free lane (overflow of the rings)
 struct BankQ {
-  unsigned long long *rec;   // [cap][3 words]; word 0 bit 63 = lap parity ("valid" flag)
+  unsigned long long *rec;   // [cap][3 words], same self-validating slots as the rings
   unsigned long long *ht;    // ht[0] = head (next to pop), ht[1] = tail (next to push)
   unsigned cap;              // power of two
   unsigned log2cap;
@@ -83,7 +83,6 @@ struct WorldCounters {
   unsigned long long sent_outer[2];  // of which across the rank boundary (NVLink)
   unsigned long long births;
   unsigned long long idle_polls, blocked_passes, bank_pushes, bank_pops;
-  unsigned long long busy_iters;     // warp-iterations that executed an event
   unsigned acc_range, pad;
 };
 
@@ -92,7 +91,7 @@ struct WorldParams {
   int V, cpw;                        // windows of this launch, CTAs per window
   float dx, minw;
   int retire_batch;
-  unsigned ring_cap;                 // records per stripe, power of two >= 32
+  unsigned ring_cap, ring_log2;      // records per stripe, power of two >= 32
   // the source (src_window < 0 on ranks that do not hold x_ini)
   int src_window;
   int src_index;                     // (int)(x_ini / dx), src/layer.cpp:106
@@ -110,7 +109,6 @@ struct WorldParams {
   // results
   unsigned long long *acc;           // the rank's tally u64[2][ncell_rank] (gacc layout)
   int ncell_rank;                    // cells of the rank + kAccExtra
-  int pad;
   WorldCounters *ctr;
 };
 
@@ -119,7 +117,7 @@ struct WorldLaunch {
   size_t smem;
 };
 
-size_t world_smem_bytes(int m_max);
+size_t world_smem_bytes(int m_max, int block);
 cudaError_t world_configure(int device, int m_max, int block, WorldLaunch *out,
                             int *max_ctas_per_sm);
 cudaError_t world_upload_jump_table(const JumpTable &jt);   // current device

@@ -79,19 +79,48 @@ struct WorldSmem {
   unsigned sent[2];
   unsigned sent_outer[2];
   unsigned births, idle_polls, blocked, bank_pushes, bank_pops, pad;
-  unsigned long long busy_iters;
   unsigned long long t_start;   // globaltimer at kernel start (for the run-time cap)
   WarpXchg wx[kWorldMaxWarps];
 };
 
-// 24-byte wire record (include/types/particle.hpp:7-18) <-> lane registers
-__device__ __forceinline__ void record_store(unsigned long long *rec, unsigned long long w0,
-                                             float x, float mu, float wmc, int idx) {
+// ---- slots of rings and banks ----------------------------------------------------------
+// A slot holds the 24-byte wire record (include/types/particle.hpp:7-18) as three 8-byte
+// words, and EACH word carries the lap parity of the slot in a bit the record never uses:
+//   word 0 = seed                      bit 63 (seeds are 63-bit, src/random.cpp:14)
+//   word 1 = x | mu << 32              bit 62 = bit 30 of mu, clear for |mu| < 2
+//   word 2 = wmc | index << 32         bit 63 = sign of the cell index, clear for index >= 0
+// A slot written in lap k of its ring carries parity (k + 1) & 1 (memory starts zeroed), so a
+// reader that expects lap k accepts a word only once the producer's store of THAT lap has
+// landed.  Every word validates itself: no ordering between the three stores is needed, hence
+// no fence and no "published count" -- the stores are plain posted writes over NVLink and the
+// consumer polls its own memory.  (Credits keep the producer from running a lap ahead.)
+__device__ __forceinline__ void slot_store(unsigned long long *rec, unsigned par,
+                                           unsigned long long seed, float x, float mu, float wmc,
+                                           int idx) {
+  st_relaxed_sys(rec, seed | ((unsigned long long)par << 63));
   st_relaxed_sys(rec + 1, (unsigned long long)__float_as_uint(x) |
-                              ((unsigned long long)__float_as_uint(mu) << 32));
+                              ((unsigned long long)(__float_as_uint(mu) | (par << 30)) << 32));
   st_relaxed_sys(rec + 2, (unsigned long long)__float_as_uint(wmc) |
-                              ((unsigned long long)(unsigned)idx << 32));
-  st_relaxed_sys(rec, w0);
+                              ((unsigned long long)((unsigned)idx | (par << 31)) << 32));
+}
+// true when all three words of the slot belong to the expected lap
+__device__ __forceinline__ bool slot_load(const unsigned long long *rec, unsigned par,
+                                          unsigned long long &a, unsigned long long &b,
+                                          unsigned long long &d) {
+  a = ld_relaxed_sys(rec);
+  if ((unsigned)(a >> 63) != par) return false;
+  b = ld_relaxed_sys(rec + 1);
+  d = ld_relaxed_sys(rec + 2);
+  return ((unsigned)(b >> 62) & 1u) == par && (unsigned)(d >> 63) == par;
+}
+__device__ __forceinline__ void slot_decode(unsigned long long a, unsigned long long b,
+                                            unsigned long long d, unsigned long long &seed,
+                                            float &x, float &mu, float &wmc, int &idx) {
+  seed = a & kMask63;
+  x = __uint_as_float((unsigned)b);
+  mu = __uint_as_float((unsigned)(b >> 32) & 0xbfffffffu);
+  wmc = __uint_as_float((unsigned)d);
+  idx = (int)((unsigned)(d >> 32) & 0x7fffffffu);
 }
 
 // every history this CTA disables is owed to the home rank's global counter; pay in batches
@@ -111,7 +140,8 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   const int cw = (int)blockIdx.x - v * p.cpw;        // CTA within the window
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int wv = cw * (int)(blockDim.x >> 5) + warp;  // stripe of this warp
+  const int nwarps = (int)(blockDim.x >> 5);
+  const int wv = cw * nwarps + warp;                 // stripe of this warp
 
   load_math_tables(&sm->math);
   {
@@ -119,11 +149,8 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(&sm->win);
     for (int i = threadIdx.x; i < (int)(sizeof(WindowDesc) / 8); i += blockDim.x) dst[i] = src[i];
   }
-  if (threadIdx.x < 16) (&sm->n_cls[0])[threadIdx.x] = 0u;   // n_cls .. pad
-  if (threadIdx.x == 0) {
-    sm->busy_iters = 0ull;
-    sm->t_start = global_timer_ns();
-  }
+  if (threadIdx.x < 14) (&sm->n_cls[0])[threadIdx.x] = 0u;   // n_cls .. pad
+  if (threadIdx.x == 0) sm->t_start = global_timer_ns();
   if (threadIdx.x < kWorldMaxWarps) {
     WarpXchg z{};
     sm->wx[threadIdx.x] = z;
@@ -133,7 +160,11 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   const int lo = sm->win.idx_lo;
   const int hi = lo + m;
   const int ncell = m + kAccExtra;
-  CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(WorldSmem));
+  // dynamic part: [source particles of each warp's current chunk] [cell constants] [tally]
+  unsigned long long *s_birth = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(WorldSmem)) +
+                                (size_t)warp * kWorkChunk;
+  CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(WorldSmem) +
+                                            (size_t)nwarps * kWorkChunk * sizeof(unsigned long long));
   unsigned *acc = reinterpret_cast<unsigned *>(s_xs + m);
   {
     const CellXs *gx = sm->win.xs;
@@ -149,8 +180,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   const unsigned lt_mask = (1u << lane) - 1u;
   const float dx = p.dx, minw = p.minw;
   const int retire_batch = p.retire_batch;
-  const unsigned cap = p.ring_cap;
-  const bool is_src = v == p.src_window;
+  const unsigned cap = p.ring_cap, ring_log2 = p.ring_log2;
   WarpXchg *wx = &sm->wx[warp];
 
   // particle state, include/types/particle.hpp:7-18, one history per lane
@@ -158,284 +188,291 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   float x = 0.f, mu = 0.f, wmc = 0.f, rmu = 0.f;
   int idx = 0;
   bool active = false;
-  bool src_done = !is_src;                        // warp-uniform: no more births to hand out
-  unsigned long long w_next = 0ull, w_end = 0ull;  // this warp's chunk of source particles
-  int cool = 0;       // iterations to wait before polling again for work that was not there
-  unsigned n_ev = 0, n_sc = 0, n_it = 0;
+  bool src_done = v != p.src_window;   // warp-uniform: no (more) births to hand out
+  unsigned w_off = 0u, w_cnt = 0u;     // this warp's chunk of source particles: next, size
+  int cool = 0;        // iterations to wait before looking again for work that was not there
+  int backoff = 2;
+  unsigned n_ev = 0, n_sc = 0;
 
   for (;;) {
     // ---- liveness: loop condition of simulate_particle, src/layer.cpp:195-197
     const bool alive = active && (wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m);
     const unsigned nolive = __ballot_sync(MCB_FULL, !alive);
-    if (nolive != 0u) {
+    // steady state: (almost) all lanes carry a live history -> one vote, straight to the event.
+    // The pass below runs once `retire_batch` lanes are without one (its cost is shared), less
+    // often while the last pass found nothing to refill them with, always when none is left.
+    if (nolive != 0u &&
+        (nolive == MCB_FULL || (__popc(nolive) >= retire_batch && --cool <= 0))) {
+      // ================================================================== the pass ==
       const bool fin = active && !alive;
       const unsigned fm = __ballot_sync(MCB_FULL, fin);
-      if (nolive == MCB_FULL || __popc(fm) >= retire_batch ||
-          (__popc(nolive) >= retire_batch && --cool <= 0)) {
-        // ================================================================ the pass ==
-        // (0) credits: tell the producers what earlier passes took out of their stripes
-        if (lane < 2) {
-          const unsigned rd = wx->rd[lane];
-          if (rd != wx->rd_pub[lane]) {
-            st_relaxed_sys(sm->win.in[lane].credit + wv, rd);
-            wx->rd_pub[lane] = rd;
-          }
+      // (0) credits: tell the producers what earlier passes took out of their stripes
+      if (lane < 2) {
+        const unsigned rd = wx->rd[lane];
+        if (rd != wx->rd_pub[lane]) {
+          st_relaxed_sys(sm->win.in[lane].credit + wv, rd);
+          wx->rd_pub[lane] = rd;
         }
-        // (1) retire: classification of src/layer.cpp:202-217, routing of :332-346
-        bool blocked = false;
-        if (fm) {
-          const int cls = (idx == lo - 1) ? 0 : (idx == hi) ? 1 : (wmc < minw) ? 2 : 0;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const bool mine = fin && cls == c;
-            const unsigned cm = __ballot_sync(MCB_FULL, mine);
-            if (cm == 0u) continue;
-            const unsigned cnt = (unsigned)__popc(cm);
-            if (sm->win.out[c].mode == 0) {
-              // global border: absorbed and counted as disabled, src/layer.cpp:350-360
-              if (mine) {
-                acc_add_smem(acc_s + (unsigned)(m + c) * 4u, acc_stride, wmc, &p.ctr->acc_range);
-                active = false;
-              }
-              if (lane == 0) {
-                atomicAdd(&sm->n_cls[c], cnt);
-                note_disabled(sm, p, cnt);
-              }
-            } else {
-              // the neighbouring window's stripe `wv`: all-or-nothing per warp and side
-              const unsigned wr = wx->wr[c];
-              unsigned cred = wx->cred[c];
-              if (wr + cnt - cred > cap) {
-                cred = __shfl_sync(MCB_FULL, ld_relaxed_sys(sm->win.out[c].credit + wv), 0);
-                if (lane == 0) wx->cred[c] = cred;
-              }
-              if (wr + cnt - cred > cap) {
-                blocked = true;   // ring full: these lanes keep their escapee and retry
-                continue;
-              }
-              if (mine) {
-                const unsigned slot = (wr + (unsigned)__popc(cm & lt_mask)) & (cap - 1u);
-                record_store(sm->win.out[c].rec + ((size_t)wv * cap + slot) * 3, seed, x, mu, wmc,
-                             idx);
-                active = false;
-              }
-              __syncwarp();
-              if (lane == 0) {
-                wx->wr[c] = wr + cnt;
-                // release: the records of ALL lanes (ordered by the __syncwarp above) are
-                // visible to whoever acquires this count
-                st_release_sys(sm->win.out[c].wr_pub + wv, wr + cnt);
-                atomicAdd(&sm->sent[c], cnt);
-                if (sm->win.out[c].outer) atomicAdd(&sm->sent_outer[c], cnt);
-              }
-              __syncwarp();
-            }
-          }
-          {
-            const bool mine = fin && cls == 2;
-            const unsigned cm = __ballot_sync(MCB_FULL, mine);
-            if (cm) {
-              if (mine) {
-                acc_add_smem(acc_s + (unsigned)(m + 2) * 4u, acc_stride, wmc, &p.ctr->acc_range);
-                active = false;
-              }
-              if (lane == 0) {
-                atomicAdd(&sm->n_cls[2], (unsigned)__popc(cm));
-                note_disabled(sm, p, (unsigned)__popc(cm));
-              }
-            }
-          }
-        }
-
-        // (2) refill idle lanes: inbound rings first, then the bank, then births
-        bool got = false;
-        unsigned im = __ballot_sync(MCB_FULL, !active);
+      }
+      // (1) retire: classification of src/layer.cpp:202-217, routing of :332-346
+      bool blocked = false;
+      if (fm) {
+        const int cls = (idx == lo - 1) ? 0 : (idx == hi) ? 1 : (wmc < minw) ? 2 : 0;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (im == 0u || !sm->win.in[c].present) continue;
-          const unsigned rd = wx->rd[c];
-          unsigned w = __shfl_sync(MCB_FULL, ld_relaxed_sys(sm->win.in[c].wr_pub + wv), 0);
-          if (w == rd) continue;
-          // acquire: pairs with the producer's release of this count
-          w = __shfl_sync(MCB_FULL, ld_acquire_sys(sm->win.in[c].wr_pub + wv), 0);
-          const unsigned avail = w - rd;
+          const bool mine = fin && cls == c;
+          const unsigned cm = __ballot_sync(MCB_FULL, mine);
+          if (cm == 0u) continue;
+          const unsigned cnt = (unsigned)__popc(cm);
+          if (sm->win.out[c].mode == 0) {
+            // global border: absorbed and counted as disabled, src/layer.cpp:350-360
+            if (mine) {
+              acc_add_smem(acc_s + (unsigned)(m + c) * 4u, acc_stride, wmc, &p.ctr->acc_range);
+              active = false;
+            }
+            if (lane == 0) {
+              atomicAdd(&sm->n_cls[c], cnt);
+              note_disabled(sm, p, cnt);
+            }
+          } else {
+            // stripe `wv` of the neighbouring window: all-or-nothing per warp and side
+            const unsigned wr = wx->wr[c];
+            unsigned cred = wx->cred[c];
+            if (wr + cnt - cred > cap) {
+              cred = __shfl_sync(MCB_FULL, ld_relaxed_sys(sm->win.out[c].credit + wv), 0);
+              if (lane == 0) wx->cred[c] = cred;
+            }
+            if (wr + cnt - cred > cap) {
+              blocked = true;   // ring full: these lanes keep their escapee and retry
+              continue;
+            }
+            if (mine) {
+              // with a neighbour on another GPU these three stores ARE the communication
+              const unsigned q = wr + (unsigned)__popc(cm & lt_mask);
+              slot_store(sm->win.out[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
+                         ((q >> ring_log2) + 1u) & 1u, seed, x, mu, wmc, idx);
+              active = false;
+            }
+            __syncwarp();
+            if (lane == 0) {
+              wx->wr[c] = wr + cnt;
+              atomicAdd(&sm->sent[c], cnt);
+              if (sm->win.out[c].outer) atomicAdd(&sm->sent_outer[c], cnt);
+            }
+            __syncwarp();
+          }
+        }
+        {
+          const bool mine = fin && cls == 2;
+          const unsigned cm = __ballot_sync(MCB_FULL, mine);
+          if (cm) {
+            if (mine) {
+              acc_add_smem(acc_s + (unsigned)(m + 2) * 4u, acc_stride, wmc, &p.ctr->acc_range);
+              active = false;
+            }
+            if (lane == 0) {
+              atomicAdd(&sm->n_cls[2], (unsigned)__popc(cm));
+              note_disabled(sm, p, (unsigned)__popc(cm));
+            }
+          }
+        }
+      }
+
+      // (2) refill idle lanes: inbound rings first, then the bank, then births
+      bool got = false;
+      unsigned im = __ballot_sync(MCB_FULL, !active);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (im == 0u || !sm->win.in[c].present) continue;
+        // idle lane number r looks at slot rd + r of this warp's stripe; the records taken are
+        // the leading run of slots that have arrived
+        const unsigned rd = wx->rd[c];
+        const unsigned r = (unsigned)__popc(im & lt_mask);
+        unsigned long long a = 0ull, b = 0ull, d = 0ull;
+        bool valid = false;
+        if (!active) {
+          const unsigned q = rd + r;
+          valid = slot_load(sm->win.in[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
+                            ((q >> ring_log2) + 1u) & 1u, a, b, d);
+        }
+        const unsigned rv = __reduce_or_sync(MCB_FULL, valid ? (1u << r) : 0u);
+        const unsigned take = rv == MCB_FULL ? 32u : (unsigned)(__ffs((int)~rv) - 1);
+        if (take == 0u) continue;
+        if (valid && r < take) {
+          slot_decode(a, b, d, seed, x, mu, wmc, idx);
+          rmu = recip_for_div(mu);
+          active = true;
+        }
+        __syncwarp();
+        if (lane == 0) wx->rd[c] = rd + take;
+        __syncwarp();
+        got = true;
+        im = __ballot_sync(MCB_FULL, !active);
+      }
+      if (im != 0u) {
+        // the window's bank (multi-consumer: claim with a CAS on the head)
+        const BankQ bq = sm->win.bank;
+        unsigned long long h = 0ull;
+        unsigned n = 0u;
+        if (lane == 0) {
           const unsigned nidle = (unsigned)__popc(im);
-          const unsigned take = avail < nidle ? avail : nidle;
+          for (;;) {
+            h = ld_relaxed_sys(bq.ht);
+            const unsigned long long t = ld_relaxed_sys(bq.ht + 1);
+            if (t <= h) break;
+            n = t - h < (unsigned long long)nidle ? (unsigned)(t - h) : nidle;
+            if (atomicCAS(bq.ht, h, h + n) == h) break;
+            n = 0u;
+          }
+        }
+        h = __shfl_sync(MCB_FULL, h, 0);
+        n = __shfl_sync(MCB_FULL, n, 0);
+        if (n) {
           const unsigned r = (unsigned)__popc(im & lt_mask);
-          if (!active && r < take) {
-            const unsigned long long *rec =
-                sm->win.in[c].rec + ((size_t)wv * cap + ((rd + r) & (cap - 1u))) * 3;
-            const unsigned long long a = ld_relaxed_sys(rec), b = ld_relaxed_sys(rec + 1),
-                                     d = ld_relaxed_sys(rec + 2);
-            seed = a;
-            x = __uint_as_float((unsigned)b);
-            mu = __uint_as_float((unsigned)(b >> 32));
-            wmc = __uint_as_float((unsigned)d);
-            idx = (int)(unsigned)(d >> 32);
+          if (!active && r < n) {
+            const unsigned long long q = h + r;
+            const unsigned long long *rec = bq.rec + (size_t)(q & (bq.cap - 1u)) * 3;
+            const unsigned par = (unsigned)(((q >> bq.log2cap) + 1ull) & 1ull);
+            unsigned long long a, b, d;
+            unsigned spins = 0u;
+            // the pusher of this slot may still be writing it (it never waits on anyone)
+            while (!slot_load(rec, par, a, b, d)) {
+              if (++spins > (1u << 22)) {   // cannot happen unless the queue was corrupted
+                atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_CAPACITY));
+                break;
+              }
+            }
+            slot_decode(a, b, d, seed, x, mu, wmc, idx);
             rmu = recip_for_div(mu);
             active = true;
+          }
+          if (lane == 0) atomicAdd(&sm->bank_pops, n);
+          got = true;
+          im = __ballot_sync(MCB_FULL, !active);
+        }
+      }
+      if (im != 0u && !src_done) {
+        // births, src/layer.cpp:101-120: particle i carries rnd_seed^(i+1)(chain_state) and
+        // consumes the first draw of its own stream for mu.  Source particles are handed to
+        // warps in chunks of kWorkChunk -- claimed only while the histories in flight
+        // (born - disabled, both counted on this rank) stay below the limit.  Claiming a
+        // chunk computes all its particle seeds at once, lane L those of particles L and
+        // L + 32 (one 63-step jump-ahead per lane and chunk), and parks them in shared memory.
+        if (w_off == w_cnt) {
+          unsigned long long base = ~0ull;
+          if (lane == 0) {
+            const unsigned long long b = ld_relaxed_sys(&p.ctrl->born);
+            if (b >= p.src_total) base = p.src_total;
+            else if (b - ld_relaxed_sys(&p.ctrl->disabled_global) < p.inflight_limit)
+              base = atomicAdd(&p.ctrl->born, (unsigned long long)kWorkChunk);
+          }
+          base = __shfl_sync(MCB_FULL, base, 0);
+          if (base != ~0ull) {
+            if (base >= p.src_total) src_done = true;
+            else {
+              const unsigned long long s = jump_state(c_seed_jump, base + 1ull + (unsigned)lane,
+                                                      p.chain_state);
+              s_birth[lane] = lcg_next(s);                                   // :112 draw #1
+              s_birth[lane + 32] = lcg_next(affine_apply(c_seed_jump.pow2[5], s));
+              __syncwarp();
+              w_off = 0u;
+              w_cnt = base + kWorkChunk <= p.src_total ? (unsigned)kWorkChunk
+                                                       : (unsigned)(p.src_total - base);
+            }
+          }
+        }
+        const unsigned avail = w_cnt - w_off;
+        const unsigned nidle = (unsigned)__popc(im);
+        const unsigned n = avail < nidle ? avail : nidle;
+        if (n) {
+          const unsigned r = (unsigned)__popc(im & lt_mask);
+          if (!active && r < n) {
+            seed = s_birth[w_off + r];
+            mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
+            rmu = recip_for_div(mu);
+            x = p.x_ini;
+            wmc = p.wmc;
+            idx = p.src_index;
+            active = true;
+          }
+          w_off += n;
+          if (lane == 0) atomicAdd(&sm->births, n);
+          got = true;
+          im = __ballot_sync(MCB_FULL, !active);
+        }
+      }
+
+      // (3) blocked senders: make room for the neighbours by moving this warp's inbound
+      // stripes into the bank -- two windows can then never wait on each other
+      if (blocked) {
+        if (lane == 0) atomicAdd(&sm->blocked, 1u);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!sm->win.in[c].present) continue;
+          const unsigned rd = wx->rd[c];
+          const unsigned q = rd + (unsigned)lane;
+          unsigned long long a, b, d;
+          const bool valid = slot_load(sm->win.in[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
+                                       ((q >> ring_log2) + 1u) & 1u, a, b, d);
+          const unsigned rv = __ballot_sync(MCB_FULL, valid);
+          const unsigned take = rv == MCB_FULL ? 32u : (unsigned)(__ffs((int)~rv) - 1);
+          if (take == 0u) continue;
+          const BankQ bq = sm->win.bank;
+          unsigned long long t = 0ull;
+          if (lane == 0) {
+            t = atomicAdd(bq.ht + 1, (unsigned long long)take);
+            if (t + take - ld_relaxed_sys(bq.ht) > (unsigned long long)bq.cap)
+              atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_CAPACITY));
+            atomicAdd(&sm->bank_pushes, take);
+          }
+          t = __shfl_sync(MCB_FULL, t, 0);
+          if ((unsigned)lane < take) {
+            unsigned long long s2;
+            float x2, mu2, w2;
+            int i2;
+            slot_decode(a, b, d, s2, x2, mu2, w2, i2);
+            const unsigned long long qb = t + (unsigned long long)lane;
+            slot_store(bq.rec + (size_t)(qb & (bq.cap - 1u)) * 3,
+                       (unsigned)(((qb >> bq.log2cap) + 1ull) & 1ull), s2, x2, mu2, w2, i2);
           }
           __syncwarp();
           if (lane == 0) wx->rd[c] = rd + take;
           __syncwarp();
-          got = true;
-          im = __ballot_sync(MCB_FULL, !active);
         }
-        if (im != 0u) {
-          // the window's bank (multi-consumer: claim with a CAS on the head)
-          const BankQ bq = sm->win.bank;
-          unsigned long long h = 0ull;
-          unsigned n = 0u;
-          if (lane == 0) {
-            const unsigned nidle = (unsigned)__popc(im);
-            for (;;) {
-              h = ld_relaxed_sys(bq.ht);
-              const unsigned long long t = ld_relaxed_sys(bq.ht + 1);
-              if (t <= h) break;
-              n = t - h < (unsigned long long)nidle ? (unsigned)(t - h) : nidle;
-              if (atomicCAS(bq.ht, h, h + n) == h) break;
-              n = 0u;
-            }
-          }
-          h = __shfl_sync(MCB_FULL, h, 0);
-          n = __shfl_sync(MCB_FULL, n, 0);
-          if (n) {
-            const unsigned r = (unsigned)__popc(im & lt_mask);
-            if (!active && r < n) {
-              const unsigned long long q = h + r;
-              const unsigned long long *rec = bq.rec + (size_t)(q & (bq.cap - 1u)) * 3;
-              const unsigned long long want = ((q >> bq.log2cap) + 1ull) & 1ull;
-              unsigned long long a;
-              unsigned spins = 0u;
-              do {  // the pusher may still be writing this slot (it never waits on anyone)
-                a = ld_acquire_sys(rec);
-                if (++spins > (1u << 24)) {  // cannot happen unless the queue was corrupted
-                  atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_CAPACITY));
-                  break;
-                }
-              } while ((a >> 63) != want);
-              const unsigned long long b = ld_relaxed_sys(rec + 1), d = ld_relaxed_sys(rec + 2);
-              seed = a & kMask63;
-              x = __uint_as_float((unsigned)b);
-              mu = __uint_as_float((unsigned)(b >> 32));
-              wmc = __uint_as_float((unsigned)d);
-              idx = (int)(unsigned)(d >> 32);
-              rmu = recip_for_div(mu);
-              active = true;
-            }
-            if (lane == 0) atomicAdd(&sm->bank_pops, n);
-            got = true;
-            im = __ballot_sync(MCB_FULL, !active);
-          }
-        }
-        if (im != 0u && !src_done) {
-          // births, src/layer.cpp:101-120: particle i carries rnd_seed^(i+1)(chain_state) and
-          // consumes the first draw of its own stream for mu.  Source particles are handed to
-          // warps in chunks of kWorkChunk; a chunk is only claimed while the number of
-          // histories in flight (born - disabled, both on this rank) is below the limit.
-          if (w_next == w_end) {
-            unsigned long long base = ~0ull;
-            if (lane == 0) {
-              const unsigned long long b = ld_relaxed_sys(&p.ctrl->born);
-              if (b >= p.src_total) base = p.src_total;
-              else if (b - ld_relaxed_sys(&p.ctrl->disabled_global) < p.inflight_limit)
-                base = atomicAdd(&p.ctrl->born, (unsigned long long)kWorkChunk);
-            }
-            base = __shfl_sync(MCB_FULL, base, 0);
-            if (base != ~0ull) {
-              if (base >= p.src_total) src_done = true;
-              else {
-                w_next = base;
-                w_end = base + kWorkChunk < p.src_total ? base + kWorkChunk : p.src_total;
-              }
-            }
-          }
-          const unsigned long long avail = w_end - w_next;
-          const unsigned nidle = (unsigned)__popc(im);
-          const unsigned n = avail < (unsigned long long)nidle ? (unsigned)avail : nidle;
-          if (n) {
-            const unsigned r = (unsigned)__popc(im & lt_mask);
-            if (!active && r < n) {
-              const unsigned long long s = jump_state(c_seed_jump, w_next + r + 1ull, p.chain_state);
-              seed = lcg_next(s);                                              // :112 draw #1
-              mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
-              rmu = recip_for_div(mu);
-              x = p.x_ini;
-              wmc = p.wmc;
-              idx = p.src_index;
-              active = true;
-            }
-            w_next += n;
-            if (lane == 0) atomicAdd(&sm->births, n);
-            got = true;
-            im = __ballot_sync(MCB_FULL, !active);
-          }
-        }
-
-        // (3) blocked senders: make room for the neighbours by moving this warp's inbound
-        // stripes into the bank -- two windows can then never wait on each other
-        if (blocked) {
-          if (lane == 0) atomicAdd(&sm->blocked, 1u);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            if (!sm->win.in[c].present) continue;
-            const unsigned rd = wx->rd[c];
-            const unsigned w = __shfl_sync(MCB_FULL, ld_acquire_sys(sm->win.in[c].wr_pub + wv), 0);
-            const unsigned avail = w - rd;
-            if (avail == 0u) continue;
-            const unsigned take = avail < 32u ? avail : 32u;
-            const BankQ bq = sm->win.bank;
-            unsigned long long t = 0ull;
-            if (lane == 0) {
-              t = atomicAdd(bq.ht + 1, (unsigned long long)take);
-              if (t + take - ld_relaxed_sys(bq.ht) > (unsigned long long)bq.cap)
-                atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_CAPACITY));
-              atomicAdd(&sm->bank_pushes, take);
-            }
-            t = __shfl_sync(MCB_FULL, t, 0);
-            if ((unsigned)lane < take) {
-              const unsigned long long *src =
-                  sm->win.in[c].rec + ((size_t)wv * cap + ((rd + (unsigned)lane) & (cap - 1u))) * 3;
-              const unsigned long long a = ld_relaxed_sys(src), b = ld_relaxed_sys(src + 1),
-                                       d = ld_relaxed_sys(src + 2);
-              const unsigned long long q = t + (unsigned long long)lane;
-              unsigned long long *dst = bq.rec + (size_t)(q & (bq.cap - 1u)) * 3;
-              st_relaxed_sys(dst + 1, b);
-              st_relaxed_sys(dst + 2, d);
-              // word 0 carries the lap parity in bit 63 (seeds are 63-bit): release = "valid"
-              st_release_sys(dst, (a & kMask63) | ((((q >> bq.log2cap) + 1ull) & 1ull) << 63));
-            }
-            __syncwarp();
-            if (lane == 0) wx->rd[c] = rd + take;
-            __syncwarp();
-          }
-        }
-
-        // (4) nothing to track (idle lanes, or escapees waiting for room in a full ring) and
-        // nothing to fetch: bookkeeping, termination, back off
-        const bool live_now = active && (wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m);
-        if (__ballot_sync(MCB_FULL, live_now) == 0u && !got) {
-          unsigned stop = 0u;
-          if (lane == 0) {
-            const unsigned owe = atomicExch(&sm->pend, 0u);
-            if (owe) red_add_sys(p.home_disabled, (unsigned long long)owe);
-            atomicAdd(&sm->idle_polls, 1u);
-            if (p.is_home && ld_relaxed_sys(&p.ctrl->disabled_global) == p.total)
-              for (int r = 0; r < p.n_ranks; ++r) st_relaxed_sys(p.done_ptrs[r], 1u);
-            stop = ld_relaxed_sys(&p.ctrl->done);
-            if (!stop && p.max_run_ns != 0ull && global_timer_ns() - sm->t_start > p.max_run_ns) {
-              // the run-time cap: a peer died or the protocol is broken -- never hang the GPU
-              atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_TIMEOUT));
-              st_relaxed_sys(&p.ctrl->done, 1u);
-              stop = 1u;
-            }
-          }
-          if (__shfl_sync(MCB_FULL, stop, 0)) break;
-          __nanosleep(500);
-        }
-        cool = (!got && __ballot_sync(MCB_FULL, !active) != 0u) ? 4 : 0;
-        continue;  // fresh lanes go through the liveness test first
       }
+
+      // (4) nothing to track (idle lanes, or escapees waiting for room in a full ring) and
+      // nothing to fetch: bookkeeping, termination, back off
+      const bool live_now = active && (wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m);
+      const unsigned lm = __ballot_sync(MCB_FULL, live_now);
+      if (lm == 0u && !got) {
+        unsigned stop = 0u;
+        if (lane == 0) {
+          const unsigned owe = atomicExch(&sm->pend, 0u);
+          if (owe) red_add_sys(p.home_disabled, (unsigned long long)owe);
+          atomicAdd(&sm->idle_polls, 1u);
+          if (p.is_home && ld_relaxed_sys(&p.ctrl->disabled_global) == p.total)
+            for (int r = 0; r < p.n_ranks; ++r) st_relaxed_sys(p.done_ptrs[r], 1u);
+          stop = ld_relaxed_sys(&p.ctrl->done);
+          if (!stop && p.max_run_ns != 0ull && global_timer_ns() - sm->t_start > p.max_run_ns) {
+            // the run-time cap: a peer died or the protocol is broken -- never hang the GPU
+            atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_TIMEOUT));
+            st_relaxed_sys(&p.ctrl->done, 1u);
+            stop = 1u;
+          }
+        }
+        if (__shfl_sync(MCB_FULL, stop, 0)) break;
+        __nanosleep(500);
+      }
+      // lanes still without a live history: look again later, ever less often (a few events)
+      if (lm != MCB_FULL && !got) {
+        cool = backoff;
+        if (backoff < 16) backoff *= 2;
+      } else {
+        cool = 0;
+        backoff = 2;
+      }
+      continue;  // fresh lanes go through the liveness test first
     }
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
@@ -444,11 +481,10 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
                        nullptr, nullptr, ncell, &p.ctr->acc_range);
       ++n_ev;
     }
-    ++n_it;
   }
 
   // ---- per-CTA flush: counters once, the CTA-private tally merged into the rank's
-  unsigned long long ev = n_ev, sc = n_sc, it = n_it;
+  unsigned long long ev = n_ev, sc = n_sc;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ev += __shfl_xor_sync(MCB_FULL, ev, o);
@@ -457,7 +493,6 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   if (lane == 0) {
     if (ev) atomicAdd(&p.ctr->events, ev);
     if (sc) atomicAdd(&p.ctr->scatters, sc);
-    if (it) atomicAdd(&sm->busy_iters, it);
   }
   __syncthreads();
   {
@@ -498,16 +533,15 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     if (sm->blocked) atomicAdd(&g->blocked_passes, (unsigned long long)sm->blocked);
     if (sm->bank_pushes) atomicAdd(&g->bank_pushes, (unsigned long long)sm->bank_pushes);
     if (sm->bank_pops) atomicAdd(&g->bank_pops, (unsigned long long)sm->bank_pops);
-    if (sm->busy_iters) atomicAdd(&g->busy_iters, sm->busy_iters);
     // anything still owed to the home counter (only on an abnormal exit)
     const unsigned owe = atomicExch(&sm->pend, 0u);
     if (owe) red_add_sys(p.home_disabled, (unsigned long long)owe);
   }
 }
 
-size_t world_smem_bytes(int m_max) {
-  return sizeof(WorldSmem) + (size_t)m_max * sizeof(CellXs) +
-         (size_t)(m_max + kAccExtra) * kAccDigits * sizeof(unsigned);
+size_t world_smem_bytes(int m_max, int block) {
+  return sizeof(WorldSmem) + (size_t)(block / 32) * kWorkChunk * sizeof(unsigned long long) +
+         (size_t)m_max * sizeof(CellXs) + (size_t)(m_max + kAccExtra) * kAccDigits * sizeof(unsigned);
 }
 
 typedef void (*WorldFn)(const WorldParams);
@@ -518,7 +552,7 @@ cudaError_t world_configure(int device, int m_max, int block, WorldLaunch *out,
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return e;
-  const size_t smem = world_smem_bytes(m_max);
+  const size_t smem = world_smem_bytes(m_max, block);
   if (smem > prop.sharedMemPerBlockOptin || block % 32 || block > 1024 || block < 32)
     return cudaErrorInvalidValue;
   e = cudaFuncSetAttribute(world_fn(block), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -201,7 +201,7 @@ def totals(results) -> dict:
     """whole-world sums of the per-rank results of one run"""
     keys = ("events", "scatters", "n_left", "n_right", "n_dead", "births", "sent_left",
             "sent_right", "window_crossings", "idle_polls", "blocked_passes", "bank_pushes",
-            "bank_pops", "busy_warp_iterations")
+            "bank_pops")
     out = {k: int(sum(r[k] for r in results)) for k in keys}
     for k in ("w_left", "w_right", "w_dead"):
         out[k] = float(sum(r[k] for r in results))
