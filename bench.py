@@ -96,12 +96,14 @@ class ClockSampler:
 
 
 def workload(n_gpus: int, particles: int | None):
+    """the N > 1 workload (N = 1: see WORKLOADS)"""
     from mc_mpi_b200 import configs
     if n_gpus == 1:
         cfg = configs.single_gpu_slab(particles or HISTORIES_1GPU)
         desc = "single-GPU single-layer slab, 1000 cells (BASELINE configs[1])"
     else:
-        cfg = configs.single_gpu_slab((particles or HISTORIES_PER_GPU * n_gpus))
+        # config.yaml physics (particle_min_weight 1e-12) scaled to 1.25e8 histories per GPU
+        cfg = configs.reference_default((particles or HISTORIES_PER_GPU * n_gpus))
         desc = f"{n_gpus}-GPU domain-decomposed slab, 1000 cells (BASELINE configs[2])"
     return cfg, desc
 
@@ -132,11 +134,17 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs and prints the reference arm
-    cfg, desc = workload(args.gpus, args.particles)
+    if args.gpus == 1:
+        make, n_default, desc, _ = WORKLOADS[args.workload]
+        cfg = make(args.particles or n_default)
+    else:
+        cfg, desc = workload(args.gpus, args.particles)
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample
+    # a bounded sample of the workload: ~1.2e9 events per step (2e6 histories of the default slab)
+    sample = args.cpu_sample or int(max(min(1.2e9 / max(cfg.events_per_history or 582.0, 1.0),
+                                            cfg.nb_particles), 200))
     for _ in range(args.warmup):
-        cpu_reference_run(cfg, max(sample // 10, 1000), cores)
+        cpu_reference_run(cfg, max(sample // 10, min(1000, sample)), cores)
     t = time.perf_counter()
     rates = []
     for _ in range(args.steps):
@@ -151,7 +159,8 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "nb_cells": cfg.nb_cells,
                    "particle_min_weight": cfg.particle_min_weight,
-                   "histories_per_step": sample},
+                   "histories_per_step": sample,
+                   "note": "a bounded sample of the GPU arm's workload (the metric is per history)"},
         "cpu_baseline": {"value": value, "unit": "histories/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} histories of the workload per step, "
                                    f"Layer::simulate(-1, {cores}) (OpenMP, one rank)"},
@@ -164,12 +173,67 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- GPU arm --
 
+def kernel_profile(kernel: str):
+    """issue-side evidence of a kernel from the committed ncu capture (profiles/r02_kernel_issue.json,
+    written by tools/ncu_summary.py from the .ncu-rep of the SAME workload): sm__issue_active,
+    warp-instructions per 32 events, DRAM bytes per history."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_kernel_issue.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def roofline_block(kernel, events, kernel_ms, launches, histories, peak, peak_src, note=""):
+    achieved = events * BYTES_PER_EVENT / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    prof = kernel_profile(kernel)
+    traffic = issue = None
+    if prof:
+        if prof.get("dram_bytes_per_history") is not None:
+            traffic = prof["dram_bytes_per_history"] * histories / max(launches, 1)
+        issue = {"achieved_pct": prof.get("issue_active_pct"),
+                 "warp_inst_per_32_events": prof.get("warp_inst_per_32_events"),
+                 "lanes_per_inst": prof.get("lanes_per_inst"), "source": prof.get("source")}
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "kernel": kernel,
+            "model": f"SURVEY 8(d) MODEL: {BYTES_PER_EVENT} B/event x events / {kernel} time "
+                     f"({launches} launches, {kernel_ms / max(launches, 1):.3f} ms avg{note}). The "
+                     "kernel keeps particle state in registers, so it does not move these bytes "
+                     "(see traffic) and frac can exceed 1; its real bound is instruction issue "
+                     "(roofline.issue).",
+            "issue": issue}
+
+
+def _configs():
+    from mc_mpi_b200 import configs
+    return configs
+
+
+WORKLOADS = {
+    # name: (config factory, default histories per step, description, path)
+    "single": (lambda n: _configs().single_gpu_slab(n),
+               HISTORIES_1GPU, "single-GPU single-layer slab, 1000 cells (BASELINE configs[1])", "layer"),
+    "default_yaml": (lambda n: _configs().reference_default(n),
+                     100_000, "config.yaml:1-10 as shipped: 1000 cells, 1e5 histories (BASELINE configs[0])",
+                     "layer"),
+    "absdom": (lambda n: _configs().absorption_dominated(n),
+               HISTORIES_1GPU, "absorption-dominated slab: sigs x100, a = 0.9 (BASELINE configs[1] variant)",
+               "layer"),
+    "thick": (lambda n: _configs().optically_thick(n),
+              10_000_000, "optically thick scattering-dominated slab: sigs x1000, a = 0.01 "
+                          "(BASELINE configs[3])", "layer"),
+    "hetero_1e6": (lambda n: _configs().heterogeneous(1_000_000, n),
+                   100_000, "heterogeneous per-cell cross-sections, 1e6 cells (BASELINE configs[4]); "
+                            "the slab is cut into shared-memory-sized windows inside the GPU", "world"),
+}
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
 
     from mc_mpi_b200 import _abi
-    from mc_mpi_b200.layer import PARTICLE_DTYPE, Layer, decompose_domain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,162 +247,105 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
-    dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    cfg, desc = workload(world, args.particles)
+        return run_world_arm(args, world, rank, local_rank)
+    return run_single_arm(args, local_rank)
+
+
+def run_single_arm(args, dev):
+    """N = 1: one layer spanning the slab on one GPU."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from mc_mpi_b200 import _abi
+    from mc_mpi_b200.layer import PARTICLE_DTYPE, Layer, decompose_domain
+    from mc_mpi_b200.worker import LocalBox
+
+    make, n_default, desc, path = WORKLOADS[args.workload]
+    cfg = make(args.particles or n_default)
     n_hist = cfg.nb_particles
     peak, peak_src = measured_hbm_peak()
     wmc = float(np.float32(1.0 / n_hist))
+    tdev = torch.device("cuda", dev)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def per_rank(x: float):
-        if dist is None:
-            return [x]
-        t = torch.zeros(world, dtype=torch.float64, device="cuda")
-        t[rank] = x
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return [round(v, 3) for v in t.tolist()]
-
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---- device-resident arm ---------------------------------------------------------
-    if world == 1:
+    if path == "layer":
         layer = decompose_domain(cfg.x_min, cfg.x_max, cfg.x_ini, 1, 0, cfg.nb_cells, n_hist,
-                                 cfg.particle_min_weight, device=local_rank, sigs=cfg.sigs,
+                                 cfg.particle_min_weight, device=dev, sigs=cfg.sigs,
                                  absorption_rates=cfg.absorption_rates)
+        stream_ptr, kernel = layer.stream_ptr, "track_kernel"
 
         def step():
             layer.create_particles(cfg.x_ini, wmc, n_hist)
             c = layer.simulate(-1)
             assert c["nb_active"] == 0
             return c
+
+        def counters():
+            c = layer.counts()
+            return {"events": c["events"], "kernel_ms": c["track_ms"], "launches": c["launches"],
+                    "gpu_launches": c["gpu_launches"]}
     else:
-        from mc_mpi_b200.world import SlabWorld, balanced_cuts
-        sw = SlabWorld(cfg, device=local_rank, nb_particles_per_cycle=args.per_cycle,
-                       ramp_from=args.ramp_from if args.ramp_from > 0 else None,
-                       overlap=args.overlap, transport=args.transport)
-        layer = sw.layer
+        # wide slab: the persistent kernel, the slab cut into windows inside the GPU
+        box = LocalBox(cfg, 1, devices=[dev])
+        box.set_option("max_run_ms", 600_000)
+        stream_ptr, kernel = box.ranks[0].stream_ptr, "world_kernel"
+        tot = {"events": 0, "kernel_ms": 0.0, "launches": 0, "gpu_launches": 0}
+        last = {}
 
         def step():
-            lay = sw.layer
-            if lay.counts()["n_unborn"] > 0 or lay.index_start <= cell_ini < lay.index_start + lay.m:
-                lay.create_particles(cfg.x_ini, wmc, n_hist)
-            base = sum_over_ranks(float(lay.counts()["nb_disabled"]))
-            sw.cfg = cfg.with_particles(int(base) + n_hist)  # disabled counts are cumulative
-            sw.spin()
-            return lay.counts()
+            r = box.run(n_hist)[0]
+            assert r["error"] == 0 and r["births"] == n_hist
+            tot["events"] += r["events"]
+            tot["kernel_ms"] += r["kernel_ms"]
+            tot["launches"] += 1
+            tot["gpu_launches"] += 1
+            last.update(r)
+            return r
 
-        cell_ini = int(np.float32(np.float32(cfg.x_ini) - np.float32(cfg.x_min)) /
-                       (np.float32(np.float32(cfg.x_max) - np.float32(cfg.x_min)) / np.float32(cfg.nb_cells)))
+        def counters():
+            return dict(tot)
 
-    for w in range(args.warmup):
-        before = sw.layer.counts()["track_ms"] if world > 1 else 0.0
+    for _ in range(args.warmup):
         step()
-        if world > 1 and args.balance and w < args.warmup - 1:
-            # measured load balancing: move the cuts so that every GPU gets the same tracking
-            # time (results do not depend on the cuts: global dx + global cross-section table)
-            cost = per_rank(sw.layer.counts()["track_ms"] - before)
-            sw.cfg = cfg
-            sw.recut(balanced_cuts(sw.cuts, cost, cfg.nb_cells))
-    if world > 1:
-        layer = sw.layer
-    stream = torch.cuda.ExternalStream(layer.stream_ptr, device=torch.device("cuda", local_rank))
-    barrier()
-    if world > 1:   # the host-side split reported below covers the timed steps only
-        sw.cycles = 0
-        sw.t_simulate = sw.t_exchange = 0.0
-        sw.t_parts = {k: 0.0 for k in sw.t_parts}
-        if os.environ.get("MCB200_TRACE_DIR"):
-            sw.trace = []
-    c0 = layer.counts()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    stream = torch.cuda.ExternalStream(stream_ptr, device=tdev)
+    torch.cuda.synchronize()
+    c0 = counters()
+    sampler = ClockSampler(dev)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     e1.record(stream)
-    barrier()
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    c1 = layer.counts()
-    events = sum_over_ranks(float(c1["events"] - c0["events"]))
-    track_ms = c1["track_ms"] - c0["track_ms"]
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    c1 = counters()
+    events = c1["events"] - c0["events"]
+    kernel_ms = c1["kernel_ms"] - c0["kernel_ms"]
     launches = c1["launches"] - c0["launches"]
-    gpu_launches = int(sum_over_ranks(float(c1["gpu_launches"] - c0["gpu_launches"])))
-    my_events = c1["events"] - c0["events"]
-    # roofline of the dominant kernel (track_kernel), this rank: algorithmic bytes / kernel time
-    achieved = my_events * BYTES_PER_EVENT / (track_ms * 1e-3) / 1e9 if track_ms > 0 else 0.0
-    achieved_min = achieved
-    if dist is not None:
-        t = torch.tensor([achieved], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        achieved_min = float(t.item())
+    gpu_launches = c1["gpu_launches"] - c0["gpu_launches"]
     value = n_hist * args.steps / (dev_ms * 1e-3)
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full`
-    # capture (bytes per history x histories per launch)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "track_kernel_dram.json")) as f:
-            per_hist = float(json.load(f)["dram_bytes_per_history"])
-        traffic = per_hist * (sum_over_ranks(float(sum(c1[k] - c0[k] for k in ("n_left", "n_right", "n_dead"))))
-                              / max(sum_over_ranks(float(launches)), 1.0))
-    except Exception:
-        pass
-    world_info = None
-    if world > 1:
-        if sw.trace is not None:
-            with open(os.path.join(os.environ["MCB200_TRACE_DIR"], f"trace_rank{rank}.json"), "w") as f:
-                json.dump({"columns": ["cycle", "simulate_ms", "track_ms_cum", "gather_ms",
-                                       "start_ms", "finish_ms", "n_out_left", "n_out_right",
-                                       "n_bank_after", "n_unborn_after"], "rows": sw.trace}, f)
-        world_info = {"cycles": sw.cycles,
-                      "t_simulate_s_max": max_over_ranks(sw.t_simulate),
-                      "t_exchange_s_max": max_over_ranks(sw.t_exchange),
-                      "track_ms_max": max_over_ranks(track_ms),
-                      "track_ms_sum": sum_over_ranks(track_ms),
-                      "track_ms_per_rank": per_rank(track_ms),
-                      "events_per_rank": per_rank(float(my_events)),
-                      "segments_per_rank": per_rank(float(
-                          sum(c1[k] - c0[k] for k in ("n_left", "n_right", "n_dead")))),
-                      "cuts": sw.cuts, "balanced": bool(args.balance and args.warmup > 1),
-                      "overlap": sw.overlap,
-                      "host_split_s_per_rank": {k: per_rank(v) for k, v in sw.t_parts.items()},
-                      "ramp_from": args.ramp_from,
-                      "note": "host wall-clock split of SlabWorld.spin over warm-up + timed steps; "
-                              "track_ms = tracking-kernel time of the timed steps"}
+    extra = None
+    if path == "world":
+        extra = {k: last[k] for k in ("windows", "ctas", "block", "stripes", "ring_cap",
+                                      "window_crossings", "idle_polls", "blocked_passes")}
+        extra["lane_utilisation"] = last["events"] / max(last["lane_slots"], 1)
 
     # ---- end-to-end arm: host buffers through the reference-facing interface ------------
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e and path == "layer":
         n_e2e = min(n_hist, args.e2e_particles)
         host = torch.empty(n_e2e * PARTICLE_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
         dx = float(layer.dx)
-        _abi.check(_abi.lib().mcb200_test_birth(local_rank, cfg.x_ini, float(np.float32(1.0 / n_e2e)),
+        _abi.check(_abi.lib().mcb200_test_birth(dev, cfg.x_ini, float(np.float32(1.0 / n_e2e)),
                                                 dx, n_e2e, 5127801, host.data_ptr()))
         e_layer = Layer(cfg.x_min, cfg.x_max, 0, cfg.nb_cells, cfg.particle_min_weight,
-                        device=local_rank, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
+                        device=dev, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
         wa = np.empty(cfg.nb_cells, dtype=np.float32)
 
         def e2e_step():
@@ -357,7 +364,6 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
         assert ce["nb_active"] == 0 and float(wa.sum()) > 0
-        import ctypes
         e2e = {"value": n_e2e * args.steps / dt, "unit": "histories/s",
                "h2d_bytes_per_step": n_e2e * PARTICLE_DTYPE.itemsize,
                "d2h_bytes_per_step": int(wa.nbytes + ctypes.sizeof(_abi.Counts)),
@@ -365,45 +371,221 @@ def run_gpu_arm(args):
                "interface": "mcb200_layer_push(host Particle[]) + mcb200_layer_simulate(-1) + "
                             "mcb200_layer_weights_absorbed (what Layer::simulate / cusimulate do)"}
         e_layer.close()
-    elif world > 1 and not args.no_e2e:
-        # N > 1: the public call sequence of a run -- register the source
-        # (Layer::create_particles takes scalars, no particle buffer), spin, gather the tally to
-        # the host like Worker::dump (src/worker.cpp:36-61) -- timed by the host clock, the
-        # read-back inside the timed region.  The host-BUFFER arm (24-byte Particle records
-        # pushed over PCIe) is what the N = 1 line measures.
-        barrier()
+    elif not args.no_e2e:
+        # the public call sequence of a whole run: config scalars in, the tally back on the host
+        wa = None
+        torch.cuda.synchronize()
         t = time.perf_counter()
         for _ in range(args.steps):
             step()
-            wa = sw.gather_weights_absorbed()
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t)
-        import ctypes
+            wa = box.gather_weights_absorbed()
+        dt = time.perf_counter() - t
+        assert float(wa.sum()) > 0
         e2e = {"value": n_hist * args.steps / dt, "unit": "histories/s",
-               "h2d_bytes_per_step": int(ctypes.sizeof(_abi.LayerDesc)),
-               "d2h_bytes_per_step": int(8 * cfg.nb_cells + world * ctypes.sizeof(_abi.Counts)),
+               "h2d_bytes_per_step": int(ctypes.sizeof(_abi.WorldDesc)),
+               "d2h_bytes_per_step": int(8 * cfg.nb_cells + ctypes.sizeof(_abi.WorldResult)),
                "histories_per_step": n_hist,
-               "interface": "decompose_domain / create_particles (scalars) + SlabWorld.spin + "
-                            "gather_weights_absorbed to the host; host-buffer arm: see N = 1"}
-        if rank == 0:
-            assert wa is not None and float(wa.sum()) > 0
-    elif world > 1:
-        e2e = {"value": None, "unit": "histories/s", "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": 0, "note": "--no-e2e"}
+               "interface": "mcb200_world_run (source particles are scalars: x_ini, n, seed) + "
+                            "mcb200_world_gather_tally_f64 to the host"}
 
-    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
+    # ---- CPU baseline (the reference's own Layer on the host cores, bounded sample) -------
     cpu = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        e_per_h = events / max(n_hist * args.steps, 1)
+        # ~20 s of CPU work: ~25 ns per event per core
+        sample = args.cpu_sample or int(max(min(20.0 * cores / (25e-9 * max(e_per_h, 1.0)), n_hist), 200))
         try:
-            rate, kind = cpu_reference_run(cfg, args.cpu_sample, cores)
+            rate, kind = cpu_reference_run(cfg, sample, cores)
             cpu = {"value": rate, "unit": "histories/s", "cores": cores, "kind": kind,
-                   "sample": f"{args.cpu_sample} histories of the same workload, "
+                   "sample": f"{sample} histories of the same workload, "
                              f"Layer::simulate(-1, {cores}) (OpenMP, one rank)"}
         except Exception as ex:  # the checker is optional for the number, never for the tests
             cpu = {"value": None, "unit": "histories/s", "cores": cores, "kind": "unavailable",
                    "sample": f"failed: {ex}"}
 
+    line = {
+        "metric": "particle histories/s (whole box)", "value": value, "unit": "histories/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "workload_key": args.workload, "nb_cells": cfg.nb_cells,
+                   "histories_per_step": n_hist,
+                   "particle_min_weight": cfg.particle_min_weight,
+                   "events_per_history": events / (n_hist * args.steps),
+                   "l2_policy": ("inputs larger than L2: the source bank is "
+                                 f"{n_hist * 24 / 1e9:.2f} GB of particle state per step"
+                                 if n_hist * 24 > 130e6 else
+                                 "source particles are born in the kernel (no input buffer); the "
+                                 "tally and cross-section tables are rewritten / re-read every step"),
+                   "parallelism": "1 GPU"},
+        "events_per_s": events / (dev_ms * 1e-3),
+        "wall_s": wall,
+        "roofline": roofline_block(kernel, events, kernel_ms, launches, n_hist * args.steps, peak,
+                                   peak_src),
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+        "world": extra,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_world_arm(args, world, rank, dev):
+    """N > 1: one process per GPU, one sub-slab per GPU, ONE resident kernel per GPU and step
+    (mcb200_world_*): escapees are stored straight into the neighbour GPU's memory over NVLink,
+    the run ends on a device-side global count.  torch.distributed carries the IPC handles at
+    start-up and holds the barrier in front of the launches -- it is not on the data path."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from mc_mpi_b200 import _abi
+    from mc_mpi_b200.worker import Worker
+    from mc_mpi_b200.world import balanced_cuts
+
+    tdev = torch.device("cuda", dev)
+    dist.init_process_group("nccl", device_id=tdev)
+    cfg, desc = workload(world, args.particles)
+    n_hist = cfg.nb_particles
+    peak, peak_src = measured_hbm_peak()
+    with open(os.path.join(ROOT, "tests", "golden", "world_digest.json")) as f:
+        digest = json.load(f)
+    parity_case = "default_slab_2e6"
+    opts = {}
+    if args.retire_batch:
+        opts["retire_batch"] = args.retire_batch
+    if args.inflight:
+        opts["inflight_limit"] = args.inflight
+    wk = Worker(cfg, device=dev, **opts)
+
+    def arm(w):
+        w.r.set_option("max_run_ms", 300_000)     # never hang the box, whatever goes wrong
+
+    arm(wk)
+    _spin = wk.spin
+
+    def spin_or_report(n=None, seed=5127801):
+        try:
+            return _spin(n, seed)
+        except _abi.McbError as ex:
+            sys.stderr.write(f"[bench] rank {rank}: run failed with cuts {wk.cuts}: {ex}\n"
+                             f"[bench] rank {rank}: counters {json.dumps(getattr(ex, 'result', None))}\n")
+            raise
+
+    wk.spin = spin_or_report
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps):
+        """`steps` whole runs, barrier + synchronize on both sides, device time = max over ranks"""
+        stream = torch.cuda.ExternalStream(wk.r.stream_ptr, device=tdev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        res = []
+        barrier()
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res.append(wk.spin(n_hist))
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = wk.all_ranks([e0.elapsed_time(e1)], "max")[0]
+        return dev_ms, wall, res
+
+    def rank_cost(r):
+        # work of a rank: events + the retire / refill cost of every history segment it served
+        segs = r["sent_left"] + r["sent_right"] + r["n_left"] + r["n_right"] + r["n_dead"]
+        return r["events"] + args.seg_cost * segs
+
+    # ---- the reference's equal split first: one warm-up, one timed step, parity ------------
+    wk.spin(n_hist)
+    eq_ms, _, eq_res = timed(1)
+    equal = {"value": n_hist / (eq_ms * 1e-3), "ms_per_step": eq_ms,
+             "cuts": "decompose_domain arithmetic (src/layer.cpp:24-27): equal cell counts",
+             "parity": wk.parity(parity_case, digest)}
+    calibration = []
+    if args.balance:
+        # measured load balancing: the result does not depend on the cuts (one global dx, one
+        # global cross-section table: bit for bit), so they go where the measured work balances
+        res = eq_res[-1]
+        for it in range(2):
+            cost = [row[0] for row in wk.all_ranks([rank_cost(res)], "table")]
+            cuts = wk.cuts or [int(c) for c in
+                               [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world)
+                                for k in range(world + 1)]]
+            new = balanced_cuts(cuts, cost, cfg.nb_cells)
+            calibration.append({"cuts": cuts, "cost_per_rank": [round(c / max(cost), 4) for c in cost]})
+            wk.recut(new)
+            arm(wk)
+            if rank == 0 and args.verbose:
+                sys.stderr.write(f"[bench] calibration {it}: cost {calibration[-1]['cost_per_rank']} -> cuts {new}\n")
+            if it == 0:
+                res = wk.spin(n_hist)
+    for _ in range(args.warmup):
+        wk.spin(n_hist)
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall, results = timed(args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_hist * args.steps / (dev_ms * 1e-3)
+    parity = wk.parity(parity_case, digest)
+
+    keys = ("events", "kernel_ms", "sent_left", "sent_right", "births", "idle_polls",
+            "blocked_passes", "bank_pushes", "lane_slots", "n_left", "n_right", "n_dead", "ctas",
+            "stripes", "ring_cap", "windows")
+    mine = [sum(r[k] for r in results) if k not in ("ctas", "stripes", "ring_cap", "windows")
+            else results[-1][k] for k in keys]
+    table = wk.all_ranks(mine, "table")
+    per = {k: [row[i] for row in table] for i, k in enumerate(keys)}
+    events = sum(per["events"])
+    kernel_ms = max(per["kernel_ms"])
+    # roofline of the dominant kernel: the rank with the fewest algorithmic bytes per kernel time
+    my_roof = mine[0] * BYTES_PER_EVENT / (mine[1] * 1e-3) / 1e9
+    roof_min = -wk.all_ranks([-my_roof], "max")[0]
+    roofline = roofline_block("world_kernel", min(per["events"]), per["kernel_ms"][per["events"].index(min(per["events"]))],
+                              args.steps, n_hist * args.steps / world, peak, peak_src,
+                              note=", the rank with the fewest events")
+    roofline["achieved"], roofline["frac"] = roof_min, roof_min / peak
+    world_info = {
+        "driver": "mcb200_world_prepare / launch / wait: ONE resident kernel per rank and step",
+        "kernel_ms_per_rank": [round(v, 3) for v in per["kernel_ms"]],
+        "events_per_rank": per["events"],
+        "lane_utilisation_per_rank": [round(e / max(s, 1), 4) for e, s in zip(per["events"], per["lane_slots"])],
+        "sent_left_per_rank": per["sent_left"], "sent_right_per_rank": per["sent_right"],
+        "idle_polls_per_rank": per["idle_polls"], "blocked_passes_per_rank": per["blocked_passes"],
+        "bank_pushes_per_rank": per["bank_pushes"],
+        "migrations_per_history": (sum(per["sent_left"]) + sum(per["sent_right"])) / (n_hist * args.steps),
+        "ctas": per["ctas"][0], "stripes": per["stripes"][0], "ring_cap": per["ring_cap"][0],
+        "cuts": wk.cuts or "equal", "balanced": bool(args.balance), "calibration": calibration,
+        "host_collectives_per_step": "1 barrier in front of the launches; none while the kernels run",
+    }
+
+    # ---- end to end: the public call sequence of a run, tally gathered to the host ----------
+    e2e = {"value": None, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+           "note": "--no-e2e"}
+    if not args.no_e2e:
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            wk.spin(n_hist)
+            wa = wk.gather_weights_absorbed()
+        barrier()
+        dt = wk.all_ranks([time.perf_counter() - t], "max")[0]
+        assert wa is not None and float(wa.sum()) > 0
+        e2e = {"value": n_hist * args.steps / dt, "unit": "histories/s",
+               "h2d_bytes_per_step": int(ctypes.sizeof(_abi.WorldDesc)),
+               "d2h_bytes_per_step": int(8 * cfg.nb_cells + world * ctypes.sizeof(_abi.WorldResult)),
+               "histories_per_step": n_hist,
+               "interface": "Worker.spin (mcb200_world_prepare / launch / wait; the source is the "
+                            "scalars x_ini, nb_particles, seed -- Layer::create_particles takes no "
+                            "particle buffer) + gather_weights_absorbed to the host like Worker::dump "
+                            "(src/worker.cpp:36-61); the host-BUFFER arm is the N = 1 line"}
+
+    ok = all(p["tally_bit_exact"] and p["counts_exact"] and p["conservation_ok"] and
+             p["kernel_error"] == 0 for p in (parity, equal["parity"]))
     if rank == 0:
         line = {
             "metric": "particle histories/s (whole box)", "value": value, "unit": "histories/s",
@@ -413,30 +595,27 @@ def run_gpu_arm(args):
             "config": {"workload": desc, "nb_cells": cfg.nb_cells, "histories_per_step": n_hist,
                        "particle_min_weight": cfg.particle_min_weight,
                        "events_per_history": events / (n_hist * args.steps),
-                       "l2_policy": "inputs larger than L2: the source bank is "
-                                    f"{n_hist * 24 / 1e9:.1f} GB of particle state per step",
-                       "parallelism": "1 GPU" if world == 1 else
-                                      f"domain decomposition, {world} sub-slabs "
-                                      f"({'cuts balanced on measured tracking time' if args.balance and args.warmup > 1 else 'equal cell counts'}), "
-                                      f"<= {args.per_cycle} source histories per cycle, escapees "
-                                      + ("stored by the tracking kernel into the neighbour GPU's "
-                                         "inbox over NVLink (CUDA IPC)" if sw.transport == "p2p"
-                                         else "shipped with ncclSend/Recv")},
+                       "l2_policy": "source particles are born in the kernel (no input buffer); "
+                                    f"{(sum(per['sent_left']) + sum(per['sent_right'])) * 24 / args.steps / 1e9:.1f} GB "
+                                    "of escapee records cross NVLink per step, each written and read once",
+                       "parallelism": f"domain decomposition, {world} sub-slabs "
+                                      f"({'cuts balanced on measured work' if args.balance else 'equal cell counts'}), "
+                                      "one persistent kernel per GPU, escapees stored by the tracking "
+                                      "kernel into the neighbour GPU's rings over NVLink (CUDA IPC), "
+                                      "device-side global count ends the run",
+                       "equal_cuts_value": equal["value"], "equal_cuts": equal},
             "events_per_s": events / (dev_ms * 1e-3),
             "wall_s": wall,
-            "roofline": {"bound": "hbm", "achieved": achieved_min, "peak": peak, "unit": "GB/s",
-                         "frac": achieved_min / peak, "traffic": traffic,
-                         "peak_source": peak_src,
-                         "model": f"{BYTES_PER_EVENT} B/event x events / track_kernel time "
-                                  f"({launches} launches, {track_ms / max(launches, 1):.3f} ms avg"
-                                  f"{', min over ranks' if world > 1 else ''})"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
+            "parity": parity,
+            "roofline": roofline,
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": world * args.steps, "clocks": clocks,
             "world": world_info,
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        sw.close()
-        dist.destroy_process_group()
+    wk.close()
+    dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: the N-GPU parity run does NOT reproduce the oracle digest")
 
 
 def main():
@@ -446,19 +625,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["mcb200", "reference"], default="mcb200")
     ap.add_argument("--particles", type=int, default=None, help="histories per step (override)")
-    ap.add_argument("--per-cycle", type=int, default=1 << 25, dest="per_cycle")
-    ap.add_argument("--ramp-from", type=int, default=1 << 20, dest="ramp_from",
-                    help="source histories of the first cycle (doubling up to --per-cycle); 0 = flat")
-    ap.add_argument("--transport", choices=["nccl", "p2p"], default="p2p",
-                    help="N > 1: nccl = outbox -> ncclSend/Recv -> bank; p2p = the tracking kernel "
-                         "stores escapees straight into the neighbour GPU's inbox over NVLink")
-    ap.add_argument("--overlap", action="store_true",
-                    help="keep the exchange of cycle c in flight under the tracking of cycle c+1")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="single",
+                    help="N = 1 only: which BASELINE configuration to run (default: configs[1])")
     ap.add_argument("--no-balance", action="store_false", dest="balance",
                     help="keep the reference's equal-cell-count decomposition")
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, dest="cpu_sample")
+    ap.add_argument("--seg-cost", type=float, default=40.0, dest="seg_cost",
+                    help="N > 1 load model: cost of one history segment in events")
+    ap.add_argument("--retire-batch", type=int, default=0, dest="retire_batch")
+    ap.add_argument("--inflight", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, dest="cpu_sample",
+                    help="histories of the CPU baseline sample (0 = about 20 s of CPU work)")
     ap.add_argument("--e2e-particles", type=int, default=HISTORIES_1GPU, dest="e2e_particles")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

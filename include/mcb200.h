@@ -213,7 +213,10 @@ int mcb200_layer_ingest_inbox(mcb200_layer *l, int32_t from_side, int32_t parity
  *   create x N; connect_local(all pairs); mcb200_world_run(worlds, N, ...)
  * Ranks in N processes (one per GPU, e.g. under torchrun / mpirun):
  *   create; export -> ship handle + geom to the other ranks (any transport) -> connect_peer;
- *   per run: prepare; <barrier across ranks>; launch; wait                                   */
+ *   per run: <barrier> prepare; <barrier>; launch; wait.  The first barrier orders "every
+ *   rank's previous wait() has returned" before anybody's prepare (which wipes the rings a
+ *   neighbour's finishing kernel may still return credits into); the second orders every
+ *   prepare before anybody's launch.                                                         */
 typedef struct mcb200_world mcb200_world;
 
 typedef struct mcb200_world_desc {
@@ -234,7 +237,7 @@ typedef struct mcb200_world_desc {
   int32_t ring_cap;          /* records per ring (power of two >= 32); 0 = auto */
   int32_t retire_batch;      /* see mcb200_layer_set_option; 0 = auto */
   int32_t reserved;
-  int64_t bank_cap;          /* records of a window's overflow bank (power of two); 0 = auto */
+  int64_t bank_cap;          /* records of one CTA's overflow bank (power of two); 0 = auto */
   int64_t inflight_limit;    /* source births pause above this many live histories; 0 = auto */
 } mcb200_world_desc;
 
@@ -257,6 +260,8 @@ typedef struct mcb200_world_result {
   int64_t sent_left, sent_right;   /* records shipped to the neighbour ranks (NVLink) */
   int64_t window_crossings;        /* records exchanged between windows inside this rank */
   int64_t idle_polls, blocked_passes, bank_pushes, bank_pops;   /* exchange diagnostics */
+  int64_t lane_slots;              /* lane x event-iteration slots offered: events / lane_slots =
+                                      fraction of lanes that carried a live history */
   double w_left, w_right, w_dead;  /* cumulative weight absorbed at the borders / by the dead */
   double kernel_ms;                /* device time of the resident kernel (CUDA events) */
   int32_t windows, ctas, block, stripes, ring_cap;
@@ -276,7 +281,7 @@ int mcb200_world_connect_peer(mcb200_world *w, int32_t peer_rank,
 int mcb200_world_connect_local(mcb200_world *w, mcb200_world *peer);
 int mcb200_world_disconnect(mcb200_world *w);
 /* a run of nb_particles source histories (seed chain from `seed`, src/layer.cpp:36):
- * prepare on EVERY rank, then a barrier across ranks, then launch, then wait. */
+ * <barrier>, prepare on EVERY rank, <barrier>, launch, wait (see above). */
 int mcb200_world_prepare(mcb200_world *w, int64_t nb_particles, uint64_t seed);
 int mcb200_world_launch(mcb200_world *w);
 int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out);

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      event_step<SHARED>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
+      event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
                          p.xs, gacc, ncell, &p.ctr->acc_range);
       ++n_ev;
     }

@@ -94,14 +94,15 @@ struct InnerLayout {
   size_t ring_bytes, cnt_bytes, link_bytes, bank_rec_bytes, bank_bytes, total;
   size_t banks_off;
 };
-InnerLayout inner_layout(int V, int S, unsigned ring_cap, unsigned bank_cap) {
+InnerLayout inner_layout(int V, int S, int cpw, unsigned ring_cap, unsigned bank_cap) {
   InnerLayout q{};
   q.ring_bytes = align256((size_t)S * ring_cap * sizeof(mcb200_particle));
   q.cnt_bytes = align256((size_t)S * sizeof(unsigned));
   q.link_bytes = 2 * (q.ring_bytes + q.cnt_bytes);
   q.banks_off = (size_t)(V > 1 ? V - 1 : 0) * q.link_bytes;
-  q.bank_rec_bytes = align256((size_t)bank_cap * sizeof(mcb200_particle));
-  q.bank_bytes = q.bank_rec_bytes + 256;   // + head / tail
+  // one bank per CTA of the window (bank_cap records each), then their cursors
+  q.bank_rec_bytes = align256((size_t)cpw * bank_cap * sizeof(mcb200_particle));
+  q.bank_bytes = q.bank_rec_bytes + align256((size_t)cpw * 2 * sizeof(unsigned));
   q.total = q.banks_off + (size_t)V * q.bank_bytes;
   return q;
 }
@@ -112,38 +113,41 @@ int choose_shape(mcb200_world *w, const mcb200_world_desc *d, int m_max_all) {
   cudaDeviceProp prop;
   MCB_CUDA(cudaGetDeviceProperties(&prop, w->device));
   const int blocks[3] = {256, 512, 1024};
-  for (int bi = 0; bi < 3; ++bi) {
-    const int block = d->block > 0 ? d->block : blocks[bi];
-    if (block % 32 || block < 32 || block > 1024)
-      return fail(MCB200_ERR_INVALID, "world: block must be a multiple of 32 in [32, 1024]");
-    const int bps = 1024 / block > 0 ? 1024 / block : 1;
-    const size_t budget = prop.sharedMemPerMultiprocessor / (size_t)bps - 1024;
-    const size_t fixed = mcb::world_smem_bytes(0, block);
-    if (budget <= fixed + 64) continue;
-    const int mw_max = (int)((budget - fixed) / (sizeof(mcb::CellXs) + mcb::kAccDigits * sizeof(unsigned)));
-    int V = d->windows > 0 ? d->windows : (m_max_all + mw_max - 1) / mw_max;
-    if (V < 1) V = 1;
-    if (V > m_max_all) V = m_max_all;
-    const int mw = (m_max_all + V - 1) / V;
-    if (mcb::world_smem_bytes(mw, block) > prop.sharedMemPerBlockOptin) {
-      if (d->block > 0 && d->windows > 0)
-        return fail(MCB200_ERR_INVALID, "world: a window does not fit shared memory");
-      if (d->block > 0) break;
-      continue;
+  // cell constants next to the tally in shared memory when the windows that fit are enough;
+  // else (sub-slabs of ~1e6 cells) the constants stay in global memory / L2: half the bytes
+  for (int xs = 1; xs >= 0; --xs) {
+    const size_t per_cell = (xs ? sizeof(mcb::CellXs) : 0) + mcb::kAccDigits * sizeof(unsigned);
+    for (int bi = 0; bi < 3; ++bi) {
+      const int block = d->block > 0 ? d->block : blocks[bi];
+      if (block % 32 || block < 32 || block > 1024)
+        return fail(MCB200_ERR_INVALID, "world: block must be a multiple of 32 in [32, 1024]");
+      const int bps = 1024 / block > 0 ? 1024 / block : 1;
+      const size_t budget = prop.sharedMemPerMultiprocessor / (size_t)bps - 1024;
+      const size_t fixed = mcb::world_smem_bytes(0, block, xs != 0);
+      if (budget <= fixed + 64) continue;
+      const int mw_max = (int)((budget - fixed) / per_cell);
+      int V = d->windows > 0 ? d->windows : (m_max_all + mw_max - 1) / mw_max;
+      if (V < 1) V = 1;
+      if (V > m_max_all) V = m_max_all;
+      const int mw = (m_max_all + V - 1) / V;
+      if (mcb::world_smem_bytes(mw, block, xs != 0) > prop.sharedMemPerBlockOptin) {
+        if (d->block > 0) break;
+        continue;
+      }
+      int per_sm = 0;
+      MCB_CUDA(mcb::world_configure(w->device, mw, block, xs != 0, &w->cfg, &per_sm));
+      int capacity = w->cfg.grid;
+      if (d->max_ctas > 0 && d->max_ctas < capacity) capacity = d->max_ctas;
+      if (V > capacity) {
+        if (d->block > 0) break;
+        continue;   // too many windows for this CTA size: try bigger CTAs (bigger windows)
+      }
+      w->V = V;
+      w->cpw = capacity / V;
+      w->cfg.grid = w->V * w->cpw;
+      w->S = w->cpw * (block / 32);
+      return MCB200_OK;
     }
-    int per_sm = 0;
-    MCB_CUDA(mcb::world_configure(w->device, mw, block, &w->cfg, &per_sm));
-    int capacity = w->cfg.grid;
-    if (d->max_ctas > 0 && d->max_ctas < capacity) capacity = d->max_ctas;
-    if (V > capacity) {
-      if (d->block > 0) break;
-      continue;   // too many windows for this CTA size: try bigger CTAs (bigger windows)
-    }
-    w->V = V;
-    w->cpw = capacity / V;
-    w->cfg.grid = w->V * w->cpw;
-    w->S = w->cpw * (block / 32);
-    return MCB200_OK;
   }
   return fail(MCB200_ERR_INVALID, "world: the sub-slab does not fit the GPU in windows "
                                   "(too many cells for the CTAs available)");
@@ -205,7 +209,7 @@ int alloc_device(mcb200_world *w) {
   q.block_bytes = (int64_t)off;
   MCB_CUDA(cudaMalloc(&w->d_xblock, off));
   MCB_CUDA(cudaMemsetAsync(w->d_xblock, 0, off, w->stream));
-  const InnerLayout il = inner_layout(w->V, w->S, w->ring_cap, w->bank_cap);
+  const InnerLayout il = inner_layout(w->V, w->S, w->cpw, w->ring_cap, w->bank_cap);
   w->inner_bytes = il.total;
   MCB_CUDA(cudaMalloc(&w->d_inner, il.total));
   MCB_CUDA(cudaMemsetAsync(w->d_inner, 0, il.total, w->stream));
@@ -239,7 +243,7 @@ int upload_windows(mcb200_world *w) {
       if (!w->peers[(size_t)k].base)
         return fail(MCB200_ERR_INVALID, "world: the home rank must be connected to every rank (missing " +
                                             std::to_string(k) + ")");
-  const InnerLayout il = inner_layout(V, w->S, w->ring_cap, w->bank_cap);
+  const InnerLayout il = inner_layout(V, w->S, w->cpw, w->ring_cap, w->bank_cap);
   auto inner_ring = [&](int b, int dir) {   // dir 0 = right-going (b -> b+1), 1 = left-going
     return w->d_inner + (size_t)b * il.link_bytes + (size_t)dir * (il.ring_bytes + il.cnt_bytes);
   };
@@ -247,10 +251,6 @@ int upload_windows(mcb200_world *w) {
   for (int v = 0; v < V; ++v) {
     mcb::WindowDesc &d = tab[(size_t)v];
     std::memset(&d, 0, sizeof d);
-    d.idx_lo = w->win_lo[(size_t)v];
-    d.m = w->win_lo[(size_t)v + 1] - w->win_lo[(size_t)v];
-    d.acc_off = d.idx_lo - w->lo;
-    d.xs = w->d_xs + d.acc_off;
     for (int s = 0; s < 2; ++s) {
       const int nv = s == 0 ? v - 1 : v + 1;        // neighbouring window inside the rank
       const int nr = s == 0 ? r - 1 : r + 1;        // neighbouring rank beyond the edge
@@ -286,7 +286,7 @@ int upload_windows(mcb200_world *w) {
     }
     unsigned char *bank = w->d_inner + il.banks_off + (size_t)v * il.bank_bytes;
     d.bank.rec = reinterpret_cast<unsigned long long *>(bank);
-    d.bank.ht = reinterpret_cast<unsigned long long *>(bank + il.bank_rec_bytes);
+    d.bank.ht = reinterpret_cast<unsigned *>(bank + il.bank_rec_bytes);
     d.bank.cap = w->bank_cap;
     d.bank.log2cap = w->bank_log2;
   }
@@ -413,39 +413,45 @@ int mcb200_world_create(const mcb200_world_desc *d, mcb200_world **out) {
   // windows of THIS rank: equal cell counts
   w->win_lo.resize((size_t)w->V + 1);
   if (w->V > w->M) return bail(fail(MCB200_ERR_INVALID, "world_create: more windows than cells"));
+  if (w->V > mcb::kWorldMaxWindows)
+    return bail(fail(MCB200_ERR_INVALID, "world_create: too many windows (" + std::to_string(w->V) + ")"));
   for (int v = 0; v <= w->V; ++v)
     w->win_lo[(size_t)v] = w->lo + (int)(((long long)w->M * v) / w->V);
   {
     int mw = 0;
     for (int v = 0; v < w->V; ++v)
       if (w->win_lo[(size_t)v + 1] - w->win_lo[(size_t)v] > mw) mw = w->win_lo[(size_t)v + 1] - w->win_lo[(size_t)v];
-    if (mcb::world_smem_bytes(mw, w->cfg.block) > w->cfg.smem)
+    if (mcb::world_smem_bytes(mw, w->cfg.block, w->cfg.xs_smem != 0) > w->cfg.smem)
       return bail(fail(MCB200_ERR_INVALID, "world_create: internal: window larger than planned"));
   }
-  // rings: ~2M records per link in total, per-stripe capacity a power of two in [64, 1024]
-  if (d->ring_cap > 0) {
-    if (d->ring_cap < 32 || (d->ring_cap & (d->ring_cap - 1)))
-      return bail(fail(MCB200_ERR_INVALID, "world_create: ring_cap must be a power of two >= 32"));
-    w->ring_cap = (unsigned)d->ring_cap;
-  } else {
-    unsigned c = pow2_ceil((2u << 20) / (unsigned)w->S);
-    w->ring_cap = c < 64 ? 64 : c > 1024 ? 1024 : c;
-  }
-  // banks: 512 MB in total, per window a power of two in [4096, 4M]
-  if (d->bank_cap > 0) {
-    if (d->bank_cap < 32 || (d->bank_cap & (d->bank_cap - 1)) || d->bank_cap > (1ll << 30))
-      return bail(fail(MCB200_ERR_INVALID, "world_create: bank_cap must be a power of two >= 32"));
-    w->bank_cap = (unsigned)d->bank_cap;
-  } else {
-    unsigned c = pow2_floor((512ull << 20) / (24ull * (unsigned long long)w->V));
-    w->bank_cap = c < 4096 ? 4096 : c > (1u << 22) ? (1u << 22) : c;
-  }
-  w->bank_log2 = ilog2(w->bank_cap);
   // histories in flight: a few per lane of the whole world keeps every GPU fed
   w->inflight_limit = d->inflight_limit > 0
                           ? (unsigned long long)d->inflight_limit
                           : 4ull * (unsigned long long)K * (unsigned long long)w->cfg.grid *
                                 (unsigned long long)w->cfg.block;
+  // rings: a stripe holds what one chain of warps (stripe s of every window of every rank) can
+  // have in flight -- the records pile up in front of the slowest window, and a full ring costs
+  // the sender its lanes -- within [64, 4096] records, at least ~2M records per link
+  if (d->ring_cap > 0) {
+    if (d->ring_cap < 32 || (d->ring_cap & (d->ring_cap - 1)))
+      return bail(fail(MCB200_ERR_INVALID, "world_create: ring_cap must be a power of two >= 32"));
+    w->ring_cap = (unsigned)d->ring_cap;
+  } else {
+    const unsigned chain = pow2_ceil(w->inflight_limit / (unsigned long long)w->S + 1ull);
+    const unsigned bulk = pow2_ceil((2u << 20) / (unsigned)w->S);
+    unsigned c = chain > bulk ? chain : bulk;
+    w->ring_cap = c < 64 ? 64 : c > 4096 ? 4096 : c;
+  }
+  // banks: 512 MB per rank in total, per CTA a power of two in [1024, 1M] records
+  if (d->bank_cap > 0) {
+    if (d->bank_cap < 32 || (d->bank_cap & (d->bank_cap - 1)) || d->bank_cap > (1ll << 30))
+      return bail(fail(MCB200_ERR_INVALID, "world_create: bank_cap must be a power of two >= 32"));
+    w->bank_cap = (unsigned)d->bank_cap;
+  } else {
+    unsigned c = pow2_floor((512ull << 20) / (24ull * (unsigned long long)w->cfg.grid));
+    w->bank_cap = c < 1024 ? 1024 : c > (1u << 20) ? (1u << 20) : c;
+  }
+  w->bank_log2 = ilog2(w->bank_cap);
   w->retire_batch = d->retire_batch > 0 ? (d->retire_batch > 32 ? 32 : d->retire_batch)
                                         : (m_max_all / w->V < 512 ? 4 : 2);
   int rc = alloc_device(w);
@@ -555,7 +561,7 @@ int mcb200_world_prepare(mcb200_world *w, int64_t nb_particles, uint64_t seed) {
   // from a zeroed ring, and the kernels count from zero); the rings are empty between runs,
   // so nothing is lost.  All ranks do this BEFORE the barrier that precedes the launches.
   MCB_CUDA(cudaMemsetAsync(w->d_xblock, 0, (size_t)w->geom.block_bytes, w->stream));
-  const InnerLayout il = inner_layout(w->V, w->S, w->ring_cap, w->bank_cap);
+  const InnerLayout il = inner_layout(w->V, w->S, w->cpw, w->ring_cap, w->bank_cap);
   if (il.banks_off > 0) MCB_CUDA(cudaMemsetAsync(w->d_inner, 0, il.banks_off, w->stream));
   // banks: head == tail between runs and the lap parity of every slot is consistent with
   // them, so they carry over; after a failed run everything is wiped
@@ -580,6 +586,9 @@ int mcb200_world_launch(mcb200_world *w) {
   p.win = w->d_win;
   p.V = w->V;
   p.cpw = w->cpw;
+  p.rank_lo = w->lo;
+  p.xs = w->d_xs;
+  for (int v = 0; v <= w->V; ++v) p.win_lo[v] = w->win_lo[(size_t)v];
   p.dx = w->dx;
   p.minw = w->minw;
   p.retire_batch = w->retire_batch;
@@ -687,6 +696,7 @@ int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out) {
     out->blocked_passes = (int64_t)c.blocked_passes;
     out->bank_pushes = (int64_t)c.bank_pushes;
     out->bank_pops = (int64_t)c.bank_pops;
+    out->lane_slots = (int64_t)c.lane_slots;
     double wc[3] = {0, 0, 0};
     int rc = fetch_world_tally(w, nullptr, wc);
     if (rc) return rc;
@@ -702,8 +712,11 @@ int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out) {
     out->error = err;
   }
   if (err == MCB200_ERR_TIMEOUT)
-    return fail(err, "world_wait: the run made no progress and was stopped (a peer rank died, or "
-                     "the kernels of the ranks never ran at the same time)");
+    return fail(err, stalled ? "world_wait: the run made no progress for stall_ms and was stopped by the "
+                               "host (a peer rank died, the kernels of the ranks never ran at the same "
+                               "time, or a rank was prepared while a neighbour's previous run was still "
+                               "ending)"
+                             : "world_wait: the kernel hit the max_run_ms cap and stopped itself");
   if (err == MCB200_ERR_CAPACITY) return fail(err, "world_wait: a window's bank overflowed (raise bank_cap)");
   if (err == MCB200_ERR_RANGE) return fail(err, "a particle weight or deposit is outside (-2^7, 2^7)");
   if (err) return fail(err, "world_wait: the kernel reported an error");

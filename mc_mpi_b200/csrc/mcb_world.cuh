@@ -18,9 +18,9 @@
 //     RmaComm's MPI_Put into the neighbour's window (src/rma_comm.cpp:133-186) with the
 //     occupancy word replaced by per-slot parity + a credit counter;
 //   * a ring that is full blocks the sending lanes (back-pressure); a warp with blocked lanes
-//     drains its own inbound stripes into the window's BANK (a multi-producer /
-//     multi-consumer queue in local memory) so that two neighbours can never wait on each
-//     other; idle lanes refill from rings, then bank, then -- in the source window -- by
+//     drains its own inbound stripes into its CTA's BANK (a multi-producer / multi-consumer
+//     queue in local memory, cursors in shared memory) so that two neighbours can never wait
+//     on each other; idle lanes refill from rings, then bank, then -- in the source window -- by
 //     giving birth to source particles in place (rnd_seed chain by LCG jump-ahead,
 //     src/layer.cpp:101-120);
 //   * termination (StateComm, src/state_comm.cpp:35-65; MPI_Allreduce,
@@ -34,6 +34,7 @@ namespace mcb {
 
 constexpr int kWorldMaxRanks = 64;
 constexpr int kWorldMaxWarps = 32;   // warps per CTA
+constexpr int kWorldMaxWindows = 640; // windows per rank (their bounds travel as kernel parameters)
 
 // what a window PRODUCES into (side 0 = towards lower cells, 1 = towards higher cells)
 struct LinkOut {
@@ -49,18 +50,18 @@ struct LinkIn {
   int present;
   int pad;
 };
-// the window's bank: records waiting for a free lane (overflow of the rings)
+// the window's banks, one per CTA serving it: records waiting for a free lane (overflow of
+// the rings).  Pushed and popped by the warps of that CTA only, so the cursors live in its
+// shared memory during a run; `ht` keeps them between runs.
 struct BankQ {
-  unsigned long long *rec;   // [cap][3 words], same self-validating slots as the rings
-  unsigned long long *ht;    // ht[0] = head (next to pop), ht[1] = tail (next to push)
-  unsigned cap;              // power of two
+  unsigned long long *rec;   // [cpw][cap][3 words], same self-validating slots as the rings
+  unsigned *ht;              // [cpw][2]: head (next to pop), tail (next to push)
+  unsigned cap;              // records per CTA, power of two
   unsigned log2cap;
 };
+// (the cells of window v are [win_lo[v], win_lo[v + 1]) of WorldParams: kernel parameters sit
+// in the constant bank, so everything derived from them is warp-uniform for the compiler)
 struct WindowDesc {
-  int idx_lo, m;             // first global cell, number of cells
-  int acc_off;               // idx_lo - first cell of the rank: offset into the rank's tally
-  int pad;
-  const CellXs *xs;          // the window's m cell constants
   LinkOut out[2];
   LinkIn in[2];
   BankQ bank;
@@ -83,12 +84,16 @@ struct WorldCounters {
   unsigned long long sent_outer[2];  // of which across the rank boundary (NVLink)
   unsigned long long births;
   unsigned long long idle_polls, blocked_passes, bank_pushes, bank_pops;
+  unsigned long long lane_slots;     // 32 x event iterations of all warps: events / lane_slots = utilisation
   unsigned acc_range, pad;
 };
 
 struct WorldParams {
   const WindowDesc *win;
   int V, cpw;                        // windows of this launch, CTAs per window
+  int rank_lo;                       // first global cell of the rank
+  int pad0;
+  const CellXs *xs;                  // the rank's cell constants (cell c at xs[c - rank_lo])
   float dx, minw;
   int retire_batch;
   unsigned ring_cap, ring_log2;      // records per stripe, power of two >= 32
@@ -110,15 +115,17 @@ struct WorldParams {
   unsigned long long *acc;           // the rank's tally u64[2][ncell_rank] (gacc layout)
   int ncell_rank;                    // cells of the rank + kAccExtra
   WorldCounters *ctr;
+  int win_lo[kWorldMaxWindows + 1];  // window v = global cells [win_lo[v], win_lo[v + 1])
 };
 
 struct WorldLaunch {
   int block, grid;
   size_t smem;
+  int xs_smem;   // cell constants in shared memory (1) or read from global memory / L2 (0)
 };
 
-size_t world_smem_bytes(int m_max, int block);
-cudaError_t world_configure(int device, int m_max, int block, WorldLaunch *out,
+size_t world_smem_bytes(int m_max, int block, bool xs_smem);
+cudaError_t world_configure(int device, int m_max, int block, bool xs_smem, WorldLaunch *out,
                             int *max_ctas_per_sm);
 cudaError_t world_upload_jump_table(const JumpTable &jt);   // current device
 cudaError_t launch_world(const WorldParams &p, const WorldLaunch &cfg, cudaStream_t stream);

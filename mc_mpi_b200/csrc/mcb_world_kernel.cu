@@ -64,11 +64,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // per-warp exchange state (warp-uniform, so it lives in shared memory, not in registers)
-struct WarpXchg {
+struct __align__(16) WarpXchg {
   unsigned wr[2];       // records this warp has stored into its outbound stripe, per side
   unsigned cred[2];     // last credit value seen for that stripe
   unsigned rd[2];       // records this warp has taken from its inbound stripe, per side
-  unsigned rd_pub[2];   // of which already returned to the producer as credit
+  // pass-only state kept out of the registers of the event loop
+  unsigned w_off, w_cnt;   // this warp's chunk of source particles: next, size
+  unsigned backoff;        // iterations to wait after a pass that found nothing (doubles to 16)
+  unsigned nap;            // ns an idle warp sleeps between looks (doubles to 2 us)
+  unsigned src_done;       // no (more) births to hand out
+  unsigned pad[5];
 };
 
 struct WorldSmem {
@@ -76,9 +81,9 @@ struct WorldSmem {
   WindowDesc win;               // this CTA's window
   unsigned n_cls[3];            // absorbed left / right, dead
   unsigned pend;                // disabled histories not yet added to the home counter
-  unsigned sent[2];
-  unsigned sent_outer[2];
-  unsigned births, idle_polls, blocked, bank_pushes, bank_pops, pad;
+  unsigned births, idle_polls, blocked, bank_pushes, bank_pops;
+  unsigned bank_head, bank_tail;   // this CTA's bank: next to pop / next to push
+  unsigned pad;
   unsigned long long t_start;   // globaltimer at kernel start (for the run-time cap)
   WarpXchg wx[kWorldMaxWarps];
 };
@@ -103,15 +108,16 @@ __device__ __forceinline__ void slot_store(unsigned long long *rec, unsigned par
   st_relaxed_sys(rec + 2, (unsigned long long)__float_as_uint(wmc) |
                               ((unsigned long long)((unsigned)idx | (par << 31)) << 32));
 }
-// true when all three words of the slot belong to the expected lap
+// the three words of a slot, loaded together (ONE round trip to the L2); true when all of
+// them belong to the expected lap
 __device__ __forceinline__ bool slot_load(const unsigned long long *rec, unsigned par,
                                           unsigned long long &a, unsigned long long &b,
                                           unsigned long long &d) {
   a = ld_relaxed_sys(rec);
-  if ((unsigned)(a >> 63) != par) return false;
   b = ld_relaxed_sys(rec + 1);
   d = ld_relaxed_sys(rec + 2);
-  return ((unsigned)(b >> 62) & 1u) == par && (unsigned)(d >> 63) == par;
+  return (unsigned)(a >> 63) == par && ((unsigned)(b >> 62) & 1u) == par &&
+         (unsigned)(d >> 63) == par;
 }
 __device__ __forceinline__ void slot_decode(unsigned long long a, unsigned long long b,
                                             unsigned long long d, unsigned long long &seed,
@@ -132,12 +138,17 @@ __device__ __forceinline__ void note_disabled(WorldSmem *sm, const WorldParams &
   }
 }
 
-template <int MAXB>
+// XS_SMEM: the window's cell constants sit next to its tally in shared memory (false: they
+// are read from global memory / L2, which halves the shared memory a cell costs -- the shape
+// chosen for sub-slabs of ~1e6 cells)
+template <int MAXB, bool XS_SMEM>
 __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const WorldParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WorldSmem *sm = reinterpret_cast<WorldSmem *>(smem_raw);
-  const int v = (int)blockIdx.x / p.cpw;             // window of this CTA
-  const int cw = (int)blockIdx.x - v * p.cpw;        // CTA within the window
+  // grid = (CTAs per window, windows): no division, so the window's bounds (kernel
+  // parameters indexed by blockIdx.y) stay in uniform registers
+  const int v = (int)blockIdx.y;                     // window of this CTA
+  const int cw = (int)blockIdx.x;                    // CTA within the window
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = (int)(blockDim.x >> 5);
@@ -149,84 +160,96 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(&sm->win);
     for (int i = threadIdx.x; i < (int)(sizeof(WindowDesc) / 8); i += blockDim.x) dst[i] = src[i];
   }
-  if (threadIdx.x < 14) (&sm->n_cls[0])[threadIdx.x] = 0u;   // n_cls .. pad
+  if (threadIdx.x < 9) (&sm->n_cls[0])[threadIdx.x] = 0u;   // n_cls .. bank_pops
   if (threadIdx.x == 0) sm->t_start = global_timer_ns();
   if (threadIdx.x < kWorldMaxWarps) {
     WarpXchg z{};
+    z.backoff = 2u;
+    z.nap = 256u;
+    z.src_done = (int)blockIdx.y != p.src_window ? 1u : 0u;
     sm->wx[threadIdx.x] = z;
   }
   __syncthreads();
-  const int m = sm->win.m;
-  const int lo = sm->win.idx_lo;
+  // this CTA's bank carries on where the last run left it (head == tail between runs)
+  if (threadIdx.x < 2) (&sm->bank_head)[threadIdx.x] = sm->win.bank.ht[2 * cw + threadIdx.x];
+  int lo = p.win_lo[v];
+  int m = p.win_lo[v + 1] - lo;
+  // opaque to the compiler: kept in registers instead of being re-read from the (indexed)
+  // parameter bank in every iteration of the event loop
+  asm volatile("" : "+r"(lo), "+r"(m));
   const int hi = lo + m;
   const int ncell = m + kAccExtra;
-  // dynamic part: [source particles of each warp's current chunk] [cell constants] [tally]
-  unsigned long long *s_birth = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(WorldSmem)) +
-                                (size_t)warp * kWorkChunk;
-  CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(WorldSmem) +
-                                            (size_t)nwarps * kWorkChunk * sizeof(unsigned long long));
-  unsigned *acc = reinterpret_cast<unsigned *>(s_xs + m);
+  // dynamic part: [cell constants] [tally] [source particles of each warp's current chunk] --
+  // the two arrays of the event first, at offsets that only depend on kernel parameters
+  CellXs *s_xs = reinterpret_cast<CellXs *>(smem_raw + sizeof(WorldSmem));
+  unsigned *acc = reinterpret_cast<unsigned *>(s_xs + (XS_SMEM ? m : 0));
+  unsigned long long *s_birth =
+      reinterpret_cast<unsigned long long *>(acc + (size_t)kAccDigits * ncell) +   // 16 B x ncell
+      (size_t)warp * kWorkChunk;
+  const CellXs *gxs = p.xs + (lo - p.rank_lo);
   {
-    const CellXs *gx = sm->win.xs;
-    for (int c = threadIdx.x; c < m; c += blockDim.x) s_xs[c] = gx[c];
+    if (XS_SMEM)
+      for (int c = threadIdx.x; c < m; c += blockDim.x) s_xs[c] = gxs[c];
     for (int c = threadIdx.x; c < kAccDigits * ncell; c += blockDim.x) acc[c] = 0u;
   }
   __syncthreads();
 
-  const unsigned tb_s = smem_addr(&sm->math);
-  const unsigned xs_s = smem_addr(s_xs);
-  const unsigned acc_s = smem_addr(acc);
+  unsigned tb_s = smem_addr(&sm->math);
+  asm volatile("" : "+r"(tb_s));   // same: the shared-window base is not re-derived per use
+  const unsigned xs_s = tb_s + (unsigned)sizeof(WorldSmem);
+  const unsigned acc_s = xs_s + (XS_SMEM ? (unsigned)m * (unsigned)sizeof(CellXs) : 0u);
   const unsigned acc_stride = (unsigned)ncell * 4u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const float dx = p.dx, minw = p.minw;
   const int retire_batch = p.retire_batch;
   const unsigned cap = p.ring_cap, ring_log2 = p.ring_log2;
   WarpXchg *wx = &sm->wx[warp];
+  // what this warp's stripes look like (warp-uniform; the compiler keeps what fits in uniform
+  // registers and re-reads the rest from shared memory)
+  const int mode0 = sm->win.out[0].mode, mode1 = sm->win.out[1].mode;
+  const int present0 = sm->win.in[0].present, present1 = sm->win.in[1].present;
+  const unsigned bank_cap = sm->win.bank.cap, bank_log2 = sm->win.bank.log2cap;
+  unsigned long long *const bank_rec = sm->win.bank.rec + (size_t)cw * bank_cap * 3;
 
   // particle state, include/types/particle.hpp:7-18, one history per lane
   unsigned long long seed = 0;
   float x = 0.f, mu = 0.f, wmc = 0.f, rmu = 0.f;
   int idx = 0;
   bool active = false;
-  bool src_done = v != p.src_window;   // warp-uniform: no (more) births to hand out
-  unsigned w_off = 0u, w_cnt = 0u;     // this warp's chunk of source particles: next, size
   int cool = 0;        // iterations to wait before looking again for work that was not there
-  int backoff = 2;
-  unsigned n_ev = 0, n_sc = 0;
+  unsigned n_ev = 0, n_sc = 0, n_it = 0;
 
   for (;;) {
     // ---- liveness: loop condition of simulate_particle, src/layer.cpp:195-197
     const bool alive = active && (wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m);
     const unsigned nolive = __ballot_sync(MCB_FULL, !alive);
-    // steady state: (almost) all lanes carry a live history -> one vote, straight to the event.
-    // The pass below runs once `retire_batch` lanes are without one (its cost is shared), less
-    // often while the last pass found nothing to refill them with, always when none is left.
-    if (nolive != 0u &&
-        (nolive == MCB_FULL || (__popc(nolive) >= retire_batch && --cool <= 0))) {
+    // steady state: (almost) all lanes carry a live history -> one vote, one compare, straight
+    // to the event.  The pass below runs once `retire_batch` (1..32) lanes are without one (its
+    // cost is shared), less often while the last pass found nothing to refill them with, always
+    // when none is left.
+    if ((unsigned)__popc(nolive) >= (unsigned)retire_batch && (nolive == MCB_FULL || --cool <= 0)) {
       // ================================================================== the pass ==
       const bool fin = active && !alive;
       const unsigned fm = __ballot_sync(MCB_FULL, fin);
-      // (0) credits: tell the producers what earlier passes took out of their stripes
-      if (lane < 2) {
-        const unsigned rd = wx->rd[lane];
-        if (rd != wx->rd_pub[lane]) {
-          st_relaxed_sys(sm->win.in[lane].credit + wv, rd);
-          wx->rd_pub[lane] = rd;
-        }
-      }
-      // (1) retire: classification of src/layer.cpp:202-217, routing of :332-346
       bool blocked = false;
+      // (1) retire: classification of src/layer.cpp:202-217, routing of :332-346
       if (fm) {
-        const int cls = (idx == lo - 1) ? 0 : (idx == hi) ? 1 : (wmc < minw) ? 2 : 0;
+        const bool goes[2] = {fin && idx == lo - 1, fin && idx == hi};
+        const unsigned m0 = __ballot_sync(MCB_FULL, goes[0]);
+        const unsigned m1 = __ballot_sync(MCB_FULL, goes[1]);
+        const unsigned md = fm & ~(m0 | m1);   // below min weight inside the window: dead
+        // this warp's outbound stripes: records stored so far / credits seen (warp-uniform)
+        unsigned wr_c[2] = {wx->wr[0], wx->wr[1]};
+        unsigned cred_c[2] = {wx->cred[0], wx->cred[1]};
+        __syncwarp();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const bool mine = fin && cls == c;
-          const unsigned cm = __ballot_sync(MCB_FULL, mine);
+          const unsigned cm = c ? m1 : m0;
           if (cm == 0u) continue;
           const unsigned cnt = (unsigned)__popc(cm);
-          if (sm->win.out[c].mode == 0) {
+          if ((c ? mode1 : mode0) == 0) {
             // global border: absorbed and counted as disabled, src/layer.cpp:350-360
-            if (mine) {
+            if (goes[c]) {
               acc_add_smem(acc_s + (unsigned)(m + c) * 4u, acc_stride, wmc, &p.ctr->acc_range);
               active = false;
             }
@@ -236,92 +259,108 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             }
           } else {
             // stripe `wv` of the neighbouring window: all-or-nothing per warp and side
-            const unsigned wr = wx->wr[c];
-            unsigned cred = wx->cred[c];
-            if (wr + cnt - cred > cap) {
-              cred = __shfl_sync(MCB_FULL, ld_relaxed_sys(sm->win.out[c].credit + wv), 0);
-              if (lane == 0) wx->cred[c] = cred;
-            }
-            if (wr + cnt - cred > cap) {
+            if (wr_c[c] + cnt - cred_c[c] > cap)   // full as far as we know: look again
+              cred_c[c] = ld_relaxed_sys(sm->win.out[c].credit + wv);
+            if (wr_c[c] + cnt - cred_c[c] > cap) {
               blocked = true;   // ring full: these lanes keep their escapee and retry
-              continue;
-            }
-            if (mine) {
-              // with a neighbour on another GPU these three stores ARE the communication
-              const unsigned q = wr + (unsigned)__popc(cm & lt_mask);
-              slot_store(sm->win.out[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
-                         ((q >> ring_log2) + 1u) & 1u, seed, x, mu, wmc, idx);
-              active = false;
-            }
-            __syncwarp();
-            if (lane == 0) {
-              wx->wr[c] = wr + cnt;
-              atomicAdd(&sm->sent[c], cnt);
-              if (sm->win.out[c].outer) atomicAdd(&sm->sent_outer[c], cnt);
-            }
-            __syncwarp();
-          }
-        }
-        {
-          const bool mine = fin && cls == 2;
-          const unsigned cm = __ballot_sync(MCB_FULL, mine);
-          if (cm) {
-            if (mine) {
-              acc_add_smem(acc_s + (unsigned)(m + 2) * 4u, acc_stride, wmc, &p.ctr->acc_range);
-              active = false;
-            }
-            if (lane == 0) {
-              atomicAdd(&sm->n_cls[2], (unsigned)__popc(cm));
-              note_disabled(sm, p, (unsigned)__popc(cm));
+            } else {
+              if (goes[c]) {
+                // with a neighbour on another GPU these three stores ARE the communication
+                const unsigned q = wr_c[c] + (unsigned)__popc(cm & lt_mask);
+                slot_store(sm->win.out[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
+                           ((q >> ring_log2) + 1u) & 1u, seed, x, mu, wmc, idx);
+                active = false;
+              }
+              wr_c[c] += cnt;
             }
           }
         }
+        if (lane == 0) {
+          wx->wr[0] = wr_c[0];
+          wx->wr[1] = wr_c[1];
+          wx->cred[0] = cred_c[0];
+          wx->cred[1] = cred_c[1];
+        }
+        if (md) {
+          if (fin && !goes[0] && !goes[1]) {
+            acc_add_smem(acc_s + (unsigned)(m + 2) * 4u, acc_stride, wmc, &p.ctr->acc_range);
+            active = false;
+          }
+          if (lane == 0) {
+            atomicAdd(&sm->n_cls[2], (unsigned)__popc(md));
+            note_disabled(sm, p, (unsigned)__popc(md));
+          }
+        }
+        __syncwarp();
       }
 
-      // (2) refill idle lanes: inbound rings first, then the bank, then births
+      // (2) refill idle lanes: inbound rings, then this CTA's bank, then births
       bool got = false;
       unsigned im = __ballot_sync(MCB_FULL, !active);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (im == 0u || !sm->win.in[c].present) continue;
-        // idle lane number r looks at slot rd + r of this warp's stripe; the records taken are
-        // the leading run of slots that have arrived
-        const unsigned rd = wx->rd[c];
+      if (im != 0u && (present0 | present1)) {
+        // ONE round trip for both sides: the idle lanes are split between the two inbound
+        // stripes in proportion to what each side has delivered so far (rd), idle lane number
+        // k of a side looks at slot rd + k of it; taken = the leading run of arrived slots
+        const unsigned rd0 = wx->rd[0], rd1 = wx->rd[1];
+        __syncwarp();
+        const unsigned nidle = (unsigned)__popc(im);
+        unsigned n1;   // idle lanes that look at side 1 (the first n1 of them)
+        if (!present0) n1 = nidle;
+        else if (!present1) n1 = 0u;
+        else {
+          const float f = __fdividef((float)rd1 + 1.0f, (float)rd0 + (float)rd1 + 2.0f);
+          n1 = (unsigned)__float2int_rn(f * (float)nidle);
+          if (nidle >= 2u) n1 = n1 < 1u ? 1u : (n1 > nidle - 1u ? nidle - 1u : n1);
+          else n1 = (rd0 + rd1 + (unsigned)n_it) & 1u;   // a single idle lane alternates
+        }
         const unsigned r = (unsigned)__popc(im & lt_mask);
+        const unsigned side = r < n1 ? 1u : 0u;
+        const unsigned k = side ? r : r - n1;
         unsigned long long a = 0ull, b = 0ull, d = 0ull;
         bool valid = false;
         if (!active) {
-          const unsigned q = rd + r;
-          valid = slot_load(sm->win.in[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
+          const unsigned q = (side ? rd1 : rd0) + k;
+          valid = slot_load(sm->win.in[side].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
                             ((q >> ring_log2) + 1u) & 1u, a, b, d);
         }
-        const unsigned rv = __reduce_or_sync(MCB_FULL, valid ? (1u << r) : 0u);
-        const unsigned take = rv == MCB_FULL ? 32u : (unsigned)(__ffs((int)~rv) - 1);
-        if (take == 0u) continue;
-        if (valid && r < take) {
+        const unsigned vm = __ballot_sync(MCB_FULL, valid);
+        const unsigned s1 = __ballot_sync(MCB_FULL, !active && side == 1u);
+        const unsigned s0 = im & ~s1;
+        const unsigned inv0 = s0 & ~vm, inv1 = s1 & ~vm;
+        // lanes below the first lane of the side whose slot has not arrived
+        const unsigned ok0 = inv0 ? (inv0 & (0u - inv0)) - 1u : MCB_FULL;
+        const unsigned ok1 = inv1 ? (inv1 & (0u - inv1)) - 1u : MCB_FULL;
+        const unsigned t0 = (unsigned)__popc(s0 & vm & ok0), t1 = (unsigned)__popc(s1 & vm & ok1);
+        if (valid && (((side ? ok1 : ok0) >> lane) & 1u)) {
           slot_decode(a, b, d, seed, x, mu, wmc, idx);
           rmu = recip_for_div(mu);
           active = true;
         }
-        __syncwarp();
-        if (lane == 0) wx->rd[c] = rd + take;
-        __syncwarp();
-        got = true;
-        im = __ballot_sync(MCB_FULL, !active);
+        if (t0 | t1) {
+          // credits straight away: the slots have been read (their values decided the branch)
+          if (lane == 0 && t0) {
+            wx->rd[0] = rd0 + t0;
+            st_relaxed_sys(sm->win.in[0].credit + wv, rd0 + t0);
+          }
+          if (lane == 1 && t1) {
+            wx->rd[1] = rd1 + t1;
+            st_relaxed_sys(sm->win.in[1].credit + wv, rd1 + t1);
+          }
+          got = true;
+          im = __ballot_sync(MCB_FULL, !active);
+        }
       }
-      if (im != 0u) {
-        // the window's bank (multi-consumer: claim with a CAS on the head)
-        const BankQ bq = sm->win.bank;
-        unsigned long long h = 0ull;
-        unsigned n = 0u;
+      if (im != 0u && *(volatile unsigned *)&sm->bank_tail != *(volatile unsigned *)&sm->bank_head) {
+        // this CTA's bank (its warps push and pop: claim with a CAS on the head)
+        unsigned h = 0u, n = 0u;
         if (lane == 0) {
           const unsigned nidle = (unsigned)__popc(im);
           for (;;) {
-            h = ld_relaxed_sys(bq.ht);
-            const unsigned long long t = ld_relaxed_sys(bq.ht + 1);
-            if (t <= h) break;
-            n = t - h < (unsigned long long)nidle ? (unsigned)(t - h) : nidle;
-            if (atomicCAS(bq.ht, h, h + n) == h) break;
+            h = *(volatile unsigned *)&sm->bank_head;
+            const unsigned avail = *(volatile unsigned *)&sm->bank_tail - h;
+            if (avail == 0u || avail > bank_cap) break;
+            n = avail < nidle ? avail : nidle;
+            if (atomicCAS(&sm->bank_head, h, h + n) == h) break;
             n = 0u;
           }
         }
@@ -330,9 +369,9 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         if (n) {
           const unsigned r = (unsigned)__popc(im & lt_mask);
           if (!active && r < n) {
-            const unsigned long long q = h + r;
-            const unsigned long long *rec = bq.rec + (size_t)(q & (bq.cap - 1u)) * 3;
-            const unsigned par = (unsigned)(((q >> bq.log2cap) + 1ull) & 1ull);
+            const unsigned q = h + r;
+            const unsigned long long *rec = bank_rec + (size_t)(q & (bank_cap - 1u)) * 3;
+            const unsigned par = ((q >> bank_log2) + 1u) & 1u;
             unsigned long long a, b, d;
             unsigned spins = 0u;
             // the pusher of this slot may still be writing it (it never waits on anyone)
@@ -351,13 +390,15 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           im = __ballot_sync(MCB_FULL, !active);
         }
       }
-      if (im != 0u && !src_done) {
+      if (im != 0u && !wx->src_done) {
         // births, src/layer.cpp:101-120: particle i carries rnd_seed^(i+1)(chain_state) and
         // consumes the first draw of its own stream for mu.  Source particles are handed to
         // warps in chunks of kWorkChunk -- claimed only while the histories in flight
         // (born - disabled, both counted on this rank) stay below the limit.  Claiming a
         // chunk computes all its particle seeds at once, lane L those of particles L and
         // L + 32 (one 63-step jump-ahead per lane and chunk), and parks them in shared memory.
+        unsigned w_off = wx->w_off, w_cnt = wx->w_cnt;
+        __syncwarp();
         if (w_off == w_cnt) {
           unsigned long long base = ~0ull;
           if (lane == 0) {
@@ -368,8 +409,9 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           }
           base = __shfl_sync(MCB_FULL, base, 0);
           if (base != ~0ull) {
-            if (base >= p.src_total) src_done = true;
-            else {
+            if (base >= p.src_total) {
+              if (lane == 0) wx->src_done = 1u;
+            } else {
               const unsigned long long s = jump_state(c_seed_jump, base + 1ull + (unsigned)lane,
                                                       p.chain_state);
               s_birth[lane] = lcg_next(s);                                   // :112 draw #1
@@ -400,15 +442,21 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           got = true;
           im = __ballot_sync(MCB_FULL, !active);
         }
+        if (lane == 0) {
+          wx->w_off = w_off;
+          wx->w_cnt = w_cnt;
+        }
+        __syncwarp();
       }
 
       // (3) blocked senders: make room for the neighbours by moving this warp's inbound
-      // stripes into the bank -- two windows can then never wait on each other
+      // stripes into the CTA's bank -- two windows can then never wait on each other
       if (blocked) {
+        __syncwarp();
         if (lane == 0) atomicAdd(&sm->blocked, 1u);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (!sm->win.in[c].present) continue;
+          if (!(c ? present1 : present0)) continue;
           const unsigned rd = wx->rd[c];
           const unsigned q = rd + (unsigned)lane;
           unsigned long long a, b, d;
@@ -417,11 +465,10 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           const unsigned rv = __ballot_sync(MCB_FULL, valid);
           const unsigned take = rv == MCB_FULL ? 32u : (unsigned)(__ffs((int)~rv) - 1);
           if (take == 0u) continue;
-          const BankQ bq = sm->win.bank;
-          unsigned long long t = 0ull;
+          unsigned t = 0u;
           if (lane == 0) {
-            t = atomicAdd(bq.ht + 1, (unsigned long long)take);
-            if (t + take - ld_relaxed_sys(bq.ht) > (unsigned long long)bq.cap)
+            t = atomicAdd(&sm->bank_tail, take);
+            if (t + take - *(volatile unsigned *)&sm->bank_head > bank_cap)
               atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_CAPACITY));
             atomicAdd(&sm->bank_pushes, take);
           }
@@ -431,12 +478,14 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             float x2, mu2, w2;
             int i2;
             slot_decode(a, b, d, s2, x2, mu2, w2, i2);
-            const unsigned long long qb = t + (unsigned long long)lane;
-            slot_store(bq.rec + (size_t)(qb & (bq.cap - 1u)) * 3,
-                       (unsigned)(((qb >> bq.log2cap) + 1ull) & 1ull), s2, x2, mu2, w2, i2);
+            const unsigned qb = t + (unsigned)lane;
+            slot_store(bank_rec + (size_t)(qb & (bank_cap - 1u)) * 3,
+                       ((qb >> bank_log2) + 1u) & 1u, s2, x2, mu2, w2, i2);
           }
-          __syncwarp();
-          if (lane == 0) wx->rd[c] = rd + take;
+          if (lane == 0) {
+            wx->rd[c] = rd + take;
+            st_relaxed_sys(sm->win.in[c].credit + wv, rd + take);
+          }
           __syncwarp();
         }
       }
@@ -462,25 +511,35 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           }
         }
         if (__shfl_sync(MCB_FULL, stop, 0)) break;
-        __nanosleep(500);
+        // an idle warp must not eat the issue slots of the warps still tracking on its SM
+        const unsigned nap = wx->nap;
+        __syncwarp();
+        __nanosleep(nap);
+        if (lane == 0 && nap < 2048u) wx->nap = nap << 1;
+      } else if (lane == 0) {
+        wx->nap = 256u;
       }
       // lanes still without a live history: look again later, ever less often (a few events)
       if (lm != MCB_FULL && !got) {
-        cool = backoff;
-        if (backoff < 16) backoff *= 2;
+        const unsigned backoff = wx->backoff;
+        __syncwarp();
+        cool = (int)backoff;
+        if (lane == 0 && backoff < 16u) wx->backoff = backoff * 2u;
       } else {
         cool = 0;
-        backoff = 2;
+        if (lane == 0) wx->backoff = 2u;
       }
+      __syncwarp();
       continue;  // fresh lanes go through the liveness test first
     }
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      event_step<true>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
-                       nullptr, nullptr, ncell, &p.ctr->acc_range);
+      event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+                                acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range);
       ++n_ev;
     }
+    ++n_it;   // lane slots offered to the event: n_ev / n_it = lane utilisation
   }
 
   // ---- per-CTA flush: counters once, the CTA-private tally merged into the rank's
@@ -493,10 +552,20 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   if (lane == 0) {
     if (ev) atomicAdd(&p.ctr->events, ev);
     if (sc) atomicAdd(&p.ctr->scatters, sc);
+    if (n_it) atomicAdd(&p.ctr->lane_slots, 32ull * n_it);
+    // records this warp pushed into its outbound stripes, per side
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const unsigned w = wx->wr[c];
+      if (w) {
+        atomicAdd(&p.ctr->sent[c], (unsigned long long)w);
+        if (sm->win.out[c].outer) atomicAdd(&p.ctr->sent_outer[c], (unsigned long long)w);
+      }
+    }
   }
   __syncthreads();
   {
-    unsigned long long *gacc = p.acc + sm->win.acc_off;
+    unsigned long long *gacc = p.acc + (lo - p.rank_lo);
     for (int c = threadIdx.x; c < m; c += blockDim.x) {
       unsigned d[kAccDigits];
       unsigned any = 0u;
@@ -524,46 +593,51 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     WorldCounters *g = p.ctr;
     for (int c = 0; c < 3; ++c)
       if (sm->n_cls[c]) atomicAdd(&g->n_cls[c], (unsigned long long)sm->n_cls[c]);
-    for (int c = 0; c < 2; ++c) {
-      if (sm->sent[c]) atomicAdd(&g->sent[c], (unsigned long long)sm->sent[c]);
-      if (sm->sent_outer[c]) atomicAdd(&g->sent_outer[c], (unsigned long long)sm->sent_outer[c]);
-    }
     if (sm->births) atomicAdd(&g->births, (unsigned long long)sm->births);
     if (sm->idle_polls) atomicAdd(&g->idle_polls, (unsigned long long)sm->idle_polls);
     if (sm->blocked) atomicAdd(&g->blocked_passes, (unsigned long long)sm->blocked);
     if (sm->bank_pushes) atomicAdd(&g->bank_pushes, (unsigned long long)sm->bank_pushes);
     if (sm->bank_pops) atomicAdd(&g->bank_pops, (unsigned long long)sm->bank_pops);
+    // the bank's cursors for the next run (head == tail unless the run was stopped)
+    sm->win.bank.ht[2 * cw] = sm->bank_head;
+    sm->win.bank.ht[2 * cw + 1] = sm->bank_tail;
     // anything still owed to the home counter (only on an abnormal exit)
     const unsigned owe = atomicExch(&sm->pend, 0u);
     if (owe) red_add_sys(p.home_disabled, (unsigned long long)owe);
   }
 }
 
-size_t world_smem_bytes(int m_max, int block) {
+size_t world_smem_bytes(int m_max, int block, bool xs_smem) {
   return sizeof(WorldSmem) + (size_t)(block / 32) * kWorkChunk * sizeof(unsigned long long) +
-         (size_t)m_max * sizeof(CellXs) + (size_t)(m_max + kAccExtra) * kAccDigits * sizeof(unsigned);
+         (xs_smem ? (size_t)m_max * sizeof(CellXs) : 0) +
+         (size_t)(m_max + kAccExtra) * kAccDigits * sizeof(unsigned) + 8;
 }
 
 typedef void (*WorldFn)(const WorldParams);
-static WorldFn world_fn(int block) { return block <= 256 ? world_kernel<256> : world_kernel<1024>; }
+static WorldFn world_fn(int block, bool xs_smem) {
+  if (block <= 256) return xs_smem ? world_kernel<256, true> : world_kernel<256, false>;
+  return xs_smem ? world_kernel<1024, true> : world_kernel<1024, false>;
+}
 
-cudaError_t world_configure(int device, int m_max, int block, WorldLaunch *out,
+cudaError_t world_configure(int device, int m_max, int block, bool xs_smem, WorldLaunch *out,
                             int *max_ctas_per_sm) {
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return e;
-  const size_t smem = world_smem_bytes(m_max, block);
+  const size_t smem = world_smem_bytes(m_max, block, xs_smem);
   if (smem > prop.sharedMemPerBlockOptin || block % 32 || block > 1024 || block < 32)
     return cudaErrorInvalidValue;
-  e = cudaFuncSetAttribute(world_fn(block), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(world_fn(block, xs_smem), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, world_fn(block), block, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, world_fn(block, xs_smem), block, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidValue;
   out->block = block;
   out->grid = prop.multiProcessorCount * per_sm;   // every CTA resident: the kernel is persistent
   out->smem = smem;
+  out->xs_smem = xs_smem ? 1 : 0;
   if (max_ctas_per_sm) *max_ctas_per_sm = per_sm;
   return cudaSuccess;
 }
@@ -573,7 +647,8 @@ cudaError_t world_upload_jump_table(const JumpTable &jt) {
 }
 
 cudaError_t launch_world(const WorldParams &p, const WorldLaunch &cfg, cudaStream_t stream) {
-  world_fn(cfg.block)<<<p.V * p.cpw, cfg.block, cfg.smem, stream>>>(p);
+  world_fn(cfg.block, cfg.xs_smem != 0)<<<dim3((unsigned)p.cpw, (unsigned)p.V), cfg.block, cfg.smem,
+                                          stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -105,7 +105,11 @@ class _Rank:
 
     def wait(self) -> dict:
         r = WorldResult()
-        check(_abi.lib().mcb200_world_wait(self._h, C.byref(r)))
+        rc = _abi.lib().mcb200_world_wait(self._h, C.byref(r))
+        if rc != _abi.OK:
+            err = _abi.McbError(rc, _abi.lib().mcb200_last_error().decode(errors="replace"))
+            err.result = r.as_dict()   # the counters of the failed run, for diagnostics
+            raise err
         return r.as_dict()
 
     def reset_tally(self):
@@ -201,7 +205,7 @@ def totals(results) -> dict:
     """whole-world sums of the per-rank results of one run"""
     keys = ("events", "scatters", "n_left", "n_right", "n_dead", "births", "sent_left",
             "sent_right", "window_crossings", "idle_polls", "blocked_passes", "bank_pushes",
-            "bank_pops")
+            "bank_pops", "lane_slots")
     out = {k: int(sum(r[k] for r in results)) for k in keys}
     for k in ("w_left", "w_right", "w_dead"):
         out[k] = float(sum(r[k] for r in results))
@@ -262,8 +266,13 @@ class Worker:
         self._connect()
 
     def spin(self, nb_particles=None, seed=SEED0) -> dict:
-        """Worker::spin: the whole run.  prepare on every rank, ONE barrier, launch, wait."""
+        """Worker::spin: the whole run.  barrier, prepare on every rank, barrier, launch, wait."""
         n = self.cfg.nb_particles if nb_particles is None else int(nb_particles)
+        if self.world_size > 1:
+            # every rank's previous kernel has ended before anybody wipes its rings: a consumer
+            # publishes its last credits (stores into the PRODUCER's memory) after the producer
+            # may already have seen `done`
+            self._dist.barrier(group=self.group)
         self.r.prepare(n, seed)
         if self.world_size > 1:
             self._dist.barrier(group=self.group)
@@ -294,6 +303,53 @@ class Worker:
         parts = [out[r, : sizes[r] * width] for r in range(K)]
         full = np.concatenate(parts)
         return full.reshape(-1, 4).astype(np.uint32) if exact else full
+
+    def all_ranks(self, values, op="sum"):
+        """element-wise sum / max / per-rank table of a few numbers over the ranks (collective)"""
+        torch, dist = self._torch, self._dist
+        v = torch.tensor([float(x) for x in values], dtype=torch.float64, device=self.tdev)
+        if self.world_size == 1:
+            return [v.tolist()] if op == "table" else v.tolist()
+        if op == "table":
+            out = torch.empty(self.world_size * v.numel(), dtype=torch.float64, device=self.tdev)
+            dist.all_gather_into_tensor(out, v, group=self.group)
+            return out.reshape(self.world_size, -1).tolist()
+        dist.all_reduce(v, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM,
+                        group=self.group)
+        return v.tolist()
+
+    def parity(self, case: str, digest: dict) -> dict:
+        """Run the digest case `case` (tests/golden/world_digest.json: what the ORACLE produces for
+        it as one layer) on this world and compare: SHA-256 over all 128 bits of every cell of the
+        gathered tally, events, scatters, histories absorbed at the global borders / dead, weight
+        conservation.  Collective; every rank gets the verdict.  The tally is reset before and
+        after (it is cumulative over runs)."""
+        import hashlib
+        want = digest[case]
+        if (want["nb_cells"], float(np.float32(want["particle_min_weight"]))) != (
+                self.cfg.nb_cells, float(np.float32(self.cfg.particle_min_weight))):
+            raise ValueError(f"digest case {case} is not this world's slab")
+        self.r.reset_tally()
+        res = self.spin(want["nb_particles"], want["seed"])
+        exact = self.gather_weights_absorbed(exact=True)
+        self.r.reset_tally()
+        ev, sc, nl, nr, nd, sl, sr, err = (int(v) for v in self.all_ranks(
+            [res[k] for k in ("events", "scatters", "n_left", "n_right", "n_dead", "sent_left",
+                              "sent_right")] + [abs(res["error"])]))
+        w_left, w_right, w_dead = self.all_ranks([res["w_left"], res["w_right"], res["w_dead"]])
+        sha = hashlib.sha256(np.ascontiguousarray(exact, dtype="<u4").tobytes()).hexdigest()
+        counts_exact = (ev, sc, nl, nr, nd) == tuple(
+            want[k] for k in ("events", "scatters", "n_left", "n_right", "n_dead"))
+        cells = exact.astype(np.float64)   # each cell's exact value rounded once to double
+        w_abs = float(np.sum(np.ldexp(cells[:, 0], -120) + np.ldexp(cells[:, 1], -88) +
+                             np.ldexp(cells[:, 2], -56) + np.ldexp(cells[:, 3], -24)))
+        conservation = w_abs + w_left + w_right + w_dead
+        return {"checked": True, "case": case, "tally_bit_exact": sha == want["tally_exact_sha256"],
+                "counts_exact": bool(counts_exact), "conservation": conservation,
+                "conservation_ok": abs(conservation - 1.0) < 1e-5, "kernel_error": err,
+                "events": ev, "migrations_per_history": (sl + sr) / want["nb_particles"],
+                "ranks": self.world_size, "cuts": self.cuts or "equal",
+                "reference": "tests/golden/world_digest.json (oracle, one layer)"}
 
     def close(self):
         if self.r is None:

@@ -6,7 +6,6 @@
 The K-rank run must reproduce the ORACLE's single-layer result committed in
 tests/golden/world_digest.json: SHA-256 of all 128 bits of every cell of the tally, events,
 scatters, histories absorbed at the global borders / dead.  Every rank exits with the same code."""
-import hashlib
 import json
 import os
 import sys
@@ -29,38 +28,6 @@ CASES = {
 }
 
 
-def world_parity(worker: Worker, case: str, digest: dict) -> dict:
-    """run `case` on the worker's world and compare with the committed oracle digest;
-    collective (every rank calls it), returns the verdict on every rank"""
-    want = digest[case]
-    res = worker.spin(want["nb_particles"], want["seed"])
-    exact = worker.gather_weights_absorbed(exact=True)
-    t = torch.tensor([res[k] for k in ("events", "scatters", "n_left", "n_right", "n_dead",
-                                       "sent_left", "sent_right", "error")],
-                     dtype=torch.int64, device=worker.tdev)
-    if worker.world_size > 1:
-        dist.all_reduce(t, group=worker.group)
-    ev, sc, nl, nr, nd, sl, sr, err = (int(v) for v in t.tolist())
-    w = torch.tensor([res["w_left"], res["w_right"], res["w_dead"]], dtype=torch.float64,
-                     device=worker.tdev)
-    if worker.world_size > 1:
-        dist.all_reduce(w, group=worker.group)
-    w_left, w_right, w_dead = (float(v) for v in w.tolist())
-    sha = hashlib.sha256(np.ascontiguousarray(exact, dtype="<u4").tobytes()).hexdigest()
-    counts_exact = (ev, sc, nl, nr, nd) == tuple(want[k] for k in ("events", "scatters", "n_left",
-                                                                   "n_right", "n_dead"))
-    # sum of the exact per-cell values (each rounded once to double) + border / dead weight
-    cells = exact.astype(np.float64)
-    w_abs = float(np.sum(np.ldexp(cells[:, 0], -120) + np.ldexp(cells[:, 1], -88) +
-                         np.ldexp(cells[:, 2], -56) + np.ldexp(cells[:, 3], -24)))
-    conservation = w_abs + w_left + w_right + w_dead
-    return {"checked": True, "case": case, "tally_bit_exact": sha == want["tally_exact_sha256"],
-            "counts_exact": bool(counts_exact), "conservation": conservation,
-            "conservation_ok": abs(conservation - 1.0) < 1e-5, "kernel_error": err,
-            "events": ev, "migrations_per_history": (sl + sr) / want["nb_particles"],
-            "reference": "tests/golden/world_digest.json (oracle, one layer)"}
-
-
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "default_slab_2e6"
     cuts_kind = sys.argv[2] if len(sys.argv) > 2 else "equal"
@@ -80,7 +47,7 @@ def main():
         cuts = edges.tolist()
     w = Worker(cfg, device=local, cuts=cuts, windows=windows)
     w.r.set_option("max_run_ms", 60_000)
-    v = world_parity(w, case, digest)
+    v = w.parity(case, digest)
     ok = v["tally_bit_exact"] and v["counts_exact"] and v["conservation_ok"] and v["kernel_error"] == 0
     if rank == 0:
         print(f"[world parity] K={K} cuts={w.cuts or 'equal'} windows={windows or 'auto'} {json.dumps(v)}",
