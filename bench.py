@@ -440,7 +440,7 @@ def run_world_arm(args, world, rank, dev):
     import torch.distributed as dist
 
     from mc_mpi_b200 import _abi
-    from mc_mpi_b200.worker import Worker
+    from mc_mpi_b200.worker import Worker, occupancy
     from mc_mpi_b200.world import balanced_cuts
 
     tdev = torch.device("cuda", dev)
@@ -499,29 +499,40 @@ def run_world_arm(args, world, rank, dev):
         segs = r["sent_left"] + r["sent_right"] + r["n_left"] + r["n_right"] + r["n_dead"]
         return r["events"] + args.seg_cost * segs
 
+    def occupancies(r):
+        return [round(row[0], 4) for row in wk.all_ranks([occupancy(r)], "table")]
+
     # ---- the reference's equal split first: one warm-up, one timed step, parity ------------
     wk.spin(n_hist)
     eq_ms, _, eq_res = timed(1)
     equal = {"value": n_hist / (eq_ms * 1e-3), "ms_per_step": eq_ms,
              "cuts": "decompose_domain arithmetic (src/layer.cpp:24-27): equal cell counts",
+             "lane_occupancy_per_rank": occupancies(eq_res[-1]),
              "parity": wk.parity(parity_case, digest)}
     calibration = []
     if args.balance:
         # measured load balancing: the result does not depend on the cuts (one global dx, one
-        # global cross-section table: bit for bit), so they go where the measured work balances
+        # global cross-section table: bit for bit), so they go where the measured work balances.
+        # First step from the work model (events + segments), then from the measured occupancy
+        # of the lanes (a rank whose lanes wait for its neighbours gets more cells).
         res = eq_res[-1]
-        for it in range(2):
-            cost = [row[0] for row in wk.all_ranks([rank_cost(res)], "table")]
-            cuts = wk.cuts or [int(c) for c in
-                               [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world)
-                                for k in range(world + 1)]]
+        for it in range(args.calibrations):
+            if it == 0:
+                cost = [row[0] for row in wk.all_ranks([rank_cost(res)], "table")]
+            else:
+                cost = occupancies(res)
+            cuts = wk.cuts or [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world)
+                               for k in range(world + 1)]
             new = balanced_cuts(cuts, cost, cfg.nb_cells)
-            calibration.append({"cuts": cuts, "cost_per_rank": [round(c / max(cost), 4) for c in cost]})
+            calibration.append({"cuts": cuts, "basis": "events + segments" if it == 0 else "lane occupancy",
+                                "cost_per_rank": [round(c / max(cost), 4) for c in cost]})
+            if new == cuts:
+                break
             wk.recut(new)
             arm(wk)
             if rank == 0 and args.verbose:
                 sys.stderr.write(f"[bench] calibration {it}: cost {calibration[-1]['cost_per_rank']} -> cuts {new}\n")
-            if it == 0:
+            if it + 1 < args.calibrations:
                 res = wk.spin(n_hist)
     for _ in range(args.warmup):
         wk.spin(n_hist)
@@ -533,6 +544,7 @@ def run_world_arm(args, world, rank, dev):
     value = n_hist * args.steps / (dev_ms * 1e-3)
     parity = wk.parity(parity_case, digest)
 
+    occ = occupancies(results[-1])
     keys = ("events", "kernel_ms", "sent_left", "sent_right", "births", "idle_polls",
             "blocked_passes", "bank_pushes", "lane_slots", "n_left", "n_right", "n_dead", "ctas",
             "stripes", "ring_cap", "windows")
@@ -554,6 +566,7 @@ def run_world_arm(args, world, rank, dev):
         "kernel_ms_per_rank": [round(v, 3) for v in per["kernel_ms"]],
         "events_per_rank": per["events"],
         "lane_utilisation_per_rank": [round(e / max(s, 1), 4) for e, s in zip(per["events"], per["lane_slots"])],
+        "lane_occupancy_per_rank": occ,
         "sent_left_per_rank": per["sent_left"], "sent_right_per_rank": per["sent_right"],
         "idle_polls_per_rank": per["idle_polls"], "blocked_passes_per_rank": per["blocked_passes"],
         "bank_pushes_per_rank": per["bank_pushes"],
@@ -629,8 +642,11 @@ def main():
                     help="N = 1 only: which BASELINE configuration to run (default: configs[1])")
     ap.add_argument("--no-balance", action="store_false", dest="balance",
                     help="keep the reference's equal-cell-count decomposition")
-    ap.add_argument("--seg-cost", type=float, default=40.0, dest="seg_cost",
+    ap.add_argument("--seg-cost", type=float, default=25.0, dest="seg_cost",
                     help="N > 1 load model: cost of one history segment in events")
+    ap.add_argument("--calibrations", type=int, default=3,
+                    help="N > 1: load-balancing steps before the warm-up (1 model-based, then "
+                         "from the measured lane occupancy)")
     ap.add_argument("--retire-batch", type=int, default=0, dest="retire_batch")
     ap.add_argument("--inflight", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, dest="cpu_sample",

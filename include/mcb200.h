@@ -262,6 +262,8 @@ typedef struct mcb200_world_result {
   int64_t idle_polls, blocked_passes, bank_pushes, bank_pops;   /* exchange diagnostics */
   int64_t lane_slots;              /* lane x event-iteration slots offered: events / lane_slots =
                                       fraction of lanes that carried a live history */
+  int64_t idle_warp_ns;            /* summed over the warps of the launch: time a warp spent without
+                                      a single live history (waiting for neighbours / the end) */
   double w_left, w_right, w_dead;  /* cumulative weight absorbed at the borders / by the dead */
   double kernel_ms;                /* device time of the resident kernel (CUDA events) */
   int32_t windows, ctas, block, stripes, ring_cap;

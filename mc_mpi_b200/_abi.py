@@ -94,6 +94,7 @@ class WorldResult(C.Structure):
         ("window_crossings", C.c_int64),
         ("idle_polls", C.c_int64), ("blocked_passes", C.c_int64),
         ("bank_pushes", C.c_int64), ("bank_pops", C.c_int64), ("lane_slots", C.c_int64),
+        ("idle_warp_ns", C.c_int64),
         ("w_left", C.c_double), ("w_right", C.c_double), ("w_dead", C.c_double),
         ("kernel_ms", C.c_double),
         ("windows", C.c_int32), ("ctas", C.c_int32), ("block", C.c_int32),

@@ -453,7 +453,7 @@ int mcb200_world_create(const mcb200_world_desc *d, mcb200_world **out) {
   }
   w->bank_log2 = ilog2(w->bank_cap);
   w->retire_batch = d->retire_batch > 0 ? (d->retire_batch > 32 ? 32 : d->retire_batch)
-                                        : (m_max_all / w->V < 512 ? 4 : 2);
+                                        : (m_max_all / w->V < 256 ? 6 : m_max_all / w->V < 512 ? 4 : 2);
   int rc = alloc_device(w);
   if (rc) return bail(rc);
   *out = w;
@@ -697,6 +697,7 @@ int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out) {
     out->bank_pushes = (int64_t)c.bank_pushes;
     out->bank_pops = (int64_t)c.bank_pops;
     out->lane_slots = (int64_t)c.lane_slots;
+    out->idle_warp_ns = (int64_t)c.idle_ns;
     double wc[3] = {0, 0, 0};
     int rc = fetch_world_tally(w, nullptr, wc);
     if (rc) return rc;

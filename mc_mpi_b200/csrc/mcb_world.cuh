@@ -85,6 +85,7 @@ struct WorldCounters {
   unsigned long long births;
   unsigned long long idle_polls, blocked_passes, bank_pushes, bank_pops;
   unsigned long long lane_slots;     // 32 x event iterations of all warps: events / lane_slots = utilisation
+  unsigned long long idle_ns;        // summed over warps: time without a single live history
   unsigned acc_range, pad;
 };
 

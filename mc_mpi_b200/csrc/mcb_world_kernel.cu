@@ -85,6 +85,7 @@ struct WorldSmem {
   unsigned bank_head, bank_tail;   // this CTA's bank: next to pop / next to push
   unsigned pad;
   unsigned long long t_start;   // globaltimer at kernel start (for the run-time cap)
+  unsigned long long idle_ns;   // time its warps spent without a single live history
   WarpXchg wx[kWorldMaxWarps];
 };
 
@@ -161,7 +162,10 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     for (int i = threadIdx.x; i < (int)(sizeof(WindowDesc) / 8); i += blockDim.x) dst[i] = src[i];
   }
   if (threadIdx.x < 9) (&sm->n_cls[0])[threadIdx.x] = 0u;   // n_cls .. bank_pops
-  if (threadIdx.x == 0) sm->t_start = global_timer_ns();
+  if (threadIdx.x == 0) {
+    sm->t_start = global_timer_ns();
+    sm->idle_ns = 0ull;
+  }
   if (threadIdx.x < kWorldMaxWarps) {
     WarpXchg z{};
     z.backoff = 2u;
@@ -232,6 +236,9 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
       const bool fin = active && !alive;
       const unsigned fm = __ballot_sync(MCB_FULL, fin);
       bool blocked = false;
+      // a warp without a single live history: the time until it has one again is idle time
+      unsigned long long t_idle0 = 0ull;
+      if (nolive == MCB_FULL && fm == 0u) t_idle0 = global_timer_ns();
       // (1) retire: classification of src/layer.cpp:202-217, routing of :332-346
       if (fm) {
         const bool goes[2] = {fin && idx == lo - 1, fin && idx == hi};
@@ -515,7 +522,10 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         const unsigned nap = wx->nap;
         __syncwarp();
         __nanosleep(nap);
-        if (lane == 0 && nap < 2048u) wx->nap = nap << 1;
+        if (lane == 0) {
+          if (nap < 2048u) wx->nap = nap << 1;
+          if (t_idle0) atomicAdd(&sm->idle_ns, global_timer_ns() - t_idle0);
+        }
       } else if (lane == 0) {
         wx->nap = 256u;
       }
@@ -595,6 +605,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
       if (sm->n_cls[c]) atomicAdd(&g->n_cls[c], (unsigned long long)sm->n_cls[c]);
     if (sm->births) atomicAdd(&g->births, (unsigned long long)sm->births);
     if (sm->idle_polls) atomicAdd(&g->idle_polls, (unsigned long long)sm->idle_polls);
+    if (sm->idle_ns) atomicAdd(&g->idle_ns, sm->idle_ns);
     if (sm->blocked) atomicAdd(&g->blocked_passes, (unsigned long long)sm->blocked);
     if (sm->bank_pushes) atomicAdd(&g->bank_pushes, (unsigned long long)sm->bank_pushes);
     if (sm->bank_pops) atomicAdd(&g->bank_pops, (unsigned long long)sm->bank_pops);

@@ -201,11 +201,19 @@ class LocalBox:
         self.close()
 
 
+def occupancy(r: dict) -> float:
+    """fraction of a rank's lane-time that carried a live history during one run: lanes busy
+    inside the event iterations x share of the time its warps had anything to track"""
+    warps = r["ctas"] * r["block"] // 32
+    idle = r["idle_warp_ns"] / max(r["kernel_ms"] * 1e6 * warps, 1.0)
+    return (r["events"] / max(r["lane_slots"], 1)) * max(1.0 - idle, 0.0)
+
+
 def totals(results) -> dict:
     """whole-world sums of the per-rank results of one run"""
     keys = ("events", "scatters", "n_left", "n_right", "n_dead", "births", "sent_left",
             "sent_right", "window_crossings", "idle_polls", "blocked_passes", "bank_pushes",
-            "bank_pops", "lane_slots")
+            "bank_pops", "lane_slots", "idle_warp_ns")
     out = {k: int(sum(r[k] for r in results)) for k in keys}
     for k in ("w_left", "w_right", "w_dead"):
         out[k] = float(sum(r[k] for r in results))

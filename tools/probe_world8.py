@@ -25,6 +25,7 @@ t, res = best
 print(json.dumps({"K": K, **opts, "cuts": cuts, "kernel_ms": round(t["kernel_ms_max"], 2),
                   "events_per_s": t["events"] / t["kernel_ms_max"] * 1e3,
                   "util": [round(r["events"] / max(r["lane_slots"], 1), 3) for r in res],
+                  "occupancy": [round(__import__("mc_mpi_b200.worker", fromlist=["x"]).occupancy(r), 3) for r in res],
                   "events_share": [round(r["events"] / t["events"] * K, 3) for r in res],
                   "idle_polls": [r["idle_polls"] for r in res],
                   "blocked": t["blocked_passes"], "ring_cap": res[0]["ring_cap"]}), flush=True)
