@@ -233,10 +233,12 @@ typedef struct mcb200_world_desc {
   const float *absorption_rates;
   int32_t windows;           /* windows per rank; 0 = as few as fit shared memory */
   int32_t block;             /* threads per CTA; 0 = auto */
-  int32_t max_ctas;          /* cap on the CTAs of the launch; 0 = fill the GPU */
+  int32_t max_ctas;          /* cap on the CTAs of the launch, counted as 256-thread CTAs (ranks that
+                                share one GPU must all be resident at once); 0 = fill the GPU */
   int32_t ring_cap;          /* records per ring (power of two >= 32); 0 = auto */
   int32_t retire_batch;      /* see mcb200_layer_set_option; 0 = auto */
-  int32_t reserved;
+  int32_t xs_global;         /* 1: keep the cell constants in global memory / L2 instead of shared
+                                memory (halves the shared memory a cell costs); 0 = only when needed */
   int64_t bank_cap;          /* records of one CTA's overflow bank (power of two); 0 = auto */
   int64_t inflight_limit;    /* source births pause above this many live histories; 0 = auto */
 } mcb200_world_desc;

@@ -73,7 +73,7 @@ class WorldDesc(C.Structure):
         ("nb_cells", C.c_int32), ("particle_min_weight", C.c_float),
         ("cuts", C.c_void_p), ("sigs", C.c_void_p), ("absorption_rates", C.c_void_p),
         ("windows", C.c_int32), ("block", C.c_int32), ("max_ctas", C.c_int32),
-        ("ring_cap", C.c_int32), ("retire_batch", C.c_int32), ("reserved", C.c_int32),
+        ("ring_cap", C.c_int32), ("retire_batch", C.c_int32), ("xs_global", C.c_int32),
         ("bank_cap", C.c_int64), ("inflight_limit", C.c_int64),
     ]
 

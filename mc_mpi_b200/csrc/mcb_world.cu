@@ -113,14 +113,20 @@ int choose_shape(mcb200_world *w, const mcb200_world_desc *d, int m_max_all) {
   cudaDeviceProp prop;
   MCB_CUDA(cudaGetDeviceProperties(&prop, w->device));
   const int blocks[3] = {256, 512, 1024};
-  // cell constants next to the tally in shared memory when the windows that fit are enough;
-  // else (sub-slabs of ~1e6 cells) the constants stay in global memory / L2: half the bytes
-  for (int xs = 1; xs >= 0; --xs) {
+  // Candidates: cell constants next to the tally in shared memory, or left in global memory /
+  // L2 (half the shared memory per cell: fewer, wider windows for sub-slabs of ~1e6 cells) x
+  // CTA size.  Taken: the shape that keeps the most lanes busy (windows x CTAs per window x
+  // threads); ties go to constants in shared memory, then to the smaller CTA.
+  long long best_lanes = -1;
+  mcb::WorldLaunch best_cfg{};
+  int best_V = 0, best_cpw = 0;
+  for (int xs = d->xs_global ? 0 : 1; xs >= 0; --xs) {
     const size_t per_cell = (xs ? sizeof(mcb::CellXs) : 0) + mcb::kAccDigits * sizeof(unsigned);
     for (int bi = 0; bi < 3; ++bi) {
       const int block = d->block > 0 ? d->block : blocks[bi];
       if (block % 32 || block < 32 || block > 1024)
         return fail(MCB200_ERR_INVALID, "world: block must be a multiple of 32 in [32, 1024]");
+      if (d->block > 0 && bi > 0) break;
       const int bps = 1024 / block > 0 ? 1024 / block : 1;
       const size_t budget = prop.sharedMemPerMultiprocessor / (size_t)bps - 1024;
       const size_t fixed = mcb::world_smem_bytes(0, block, xs != 0);
@@ -130,27 +136,49 @@ int choose_shape(mcb200_world *w, const mcb200_world_desc *d, int m_max_all) {
       if (V < 1) V = 1;
       if (V > m_max_all) V = m_max_all;
       const int mw = (m_max_all + V - 1) / V;
-      if (mcb::world_smem_bytes(mw, block, xs != 0) > prop.sharedMemPerBlockOptin) {
-        if (d->block > 0) break;
-        continue;
-      }
+      if (mcb::world_smem_bytes(mw, block, xs != 0) > prop.sharedMemPerBlockOptin) continue;
+      mcb::WorldLaunch cfg{};
       int per_sm = 0;
-      MCB_CUDA(mcb::world_configure(w->device, mw, block, xs != 0, &w->cfg, &per_sm));
-      int capacity = w->cfg.grid;
-      if (d->max_ctas > 0 && d->max_ctas < capacity) capacity = d->max_ctas;
-      if (V > capacity) {
-        if (d->block > 0) break;
-        continue;   // too many windows for this CTA size: try bigger CTAs (bigger windows)
+      MCB_CUDA(mcb::world_configure(w->device, mw, block, xs != 0, &cfg, &per_sm));
+      int capacity = cfg.grid;
+      if (d->max_ctas > 0) {   // the caller's cap counts 256-thread CTAs
+        const int cap_b = d->max_ctas * 256 / block > 0 ? d->max_ctas * 256 / block : 1;
+        if (cap_b < capacity) capacity = cap_b;
       }
-      w->V = V;
-      w->cpw = capacity / V;
-      w->cfg.grid = w->V * w->cpw;
-      w->S = w->cpw * (block / 32);
-      return MCB200_OK;
+      if (V > capacity || V > mcb::kWorldMaxWindows) continue;   // too many windows for this CTA size
+      const int cpw = capacity / V;
+      if (d->windows <= 0 && V > 1) {
+        // more, narrower windows than shared memory demands if that fills the CTA slots the
+        // division left over (e.g. 320 windows needed, 592 slots: 592 windows of one CTA)
+        int Vf = capacity / cpw;
+        if (Vf > mcb::kWorldMaxWindows) Vf = mcb::kWorldMaxWindows;
+        if (Vf > m_max_all) Vf = m_max_all;
+        if (Vf > V) V = Vf;
+      }
+      const long long lanes = (long long)V * cpw * block;
+      if (lanes > best_lanes) {
+        best_lanes = lanes;
+        best_cfg = cfg;
+        best_V = V;
+        best_cpw = cpw;
+      }
     }
   }
-  return fail(MCB200_ERR_INVALID, "world: the sub-slab does not fit the GPU in windows "
-                                  "(too many cells for the CTAs available)");
+  if (best_lanes < 0)
+    return fail(MCB200_ERR_INVALID, "world: the sub-slab does not fit the GPU in windows "
+                                    "(too many cells for the CTAs available)");
+  w->cfg = best_cfg;
+  w->V = best_V;
+  w->cpw = best_cpw;
+  w->cfg.grid = w->V * w->cpw;
+  w->S = w->cpw * (w->cfg.block / 32);
+  // (re)apply the launch attributes of the chosen variant
+  int per_sm = 0;
+  const int mw = (m_max_all + w->V - 1) / w->V;
+  mcb::WorldLaunch again{};
+  MCB_CUDA(mcb::world_configure(w->device, mw, w->cfg.block, w->cfg.xs_smem != 0, &again, &per_sm));
+  w->cfg.smem = again.smem;
+  return MCB200_OK;
 }
 
 void free_device(mcb200_world *w) {
@@ -657,7 +685,11 @@ int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out) {
           seen[1] = w->h_prog[1];
           last_move = now;
         } else if (!stalled && now - last_move > std::chrono::milliseconds(w->stall_ms)) {
-          const unsigned flags[2] = {1u, (unsigned)(-MCB200_ERR_TIMEOUT)};   // done, error
+          // stop this rank's kernel; an error it raised itself (a bank overflow ...) is kept
+          unsigned flags[2] = {1u, 0u};   // done, error
+          cudaMemcpyAsync(&flags[1], &mine->error, sizeof(unsigned), cudaMemcpyDeviceToHost, w->side);
+          cudaStreamSynchronize(w->side);
+          if (flags[1] == 0u) flags[1] = (unsigned)(-MCB200_ERR_TIMEOUT);
           cudaMemcpyAsync(&mine->done, flags, sizeof flags, cudaMemcpyHostToDevice, w->side);
           cudaStreamSynchronize(w->side);
           stalled = true;

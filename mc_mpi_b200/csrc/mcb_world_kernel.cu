@@ -405,8 +405,24 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         // chunk computes all its particle seeds at once, lane L those of particles L and
         // L + 32 (one 63-step jump-ahead per lane and chunk), and parks them in shared memory.
         unsigned w_off = wx->w_off, w_cnt = wx->w_cnt;
+        // pacing: no births while one of this warp's outbound stripes is more than half full --
+        // the source follows the rate its neighbours take records at instead of running into a
+        // full ring (which would cost it its lanes) or flooding the banks downstream
+        bool room = true;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if ((c ? mode1 : mode0) == 0) continue;
+          const unsigned wr = wx->wr[c];
+          unsigned cred = wx->cred[c];
+          if (wr - cred > (cap >> 1)) {
+            cred = ld_relaxed_sys(sm->win.out[c].credit + wv);
+            __syncwarp();
+            if (lane == 0) wx->cred[c] = cred;
+            if (wr - cred > (cap >> 1)) room = false;
+          }
+        }
         __syncwarp();
-        if (w_off == w_cnt) {
+        if (w_off == w_cnt && room) {
           unsigned long long base = ~0ull;
           if (lane == 0) {
             const unsigned long long b = ld_relaxed_sys(&p.ctrl->born);
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             }
           }
         }
-        const unsigned avail = w_cnt - w_off;
+        const unsigned avail = room ? w_cnt - w_off : 0u;
         const unsigned nidle = (unsigned)__popc(im);
         const unsigned n = avail < nidle ? avail : nidle;
         if (n) {

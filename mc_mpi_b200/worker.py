@@ -44,7 +44,7 @@ def _desc(cfg: _configs.SlabConfig, rank, world_size, device, cuts, opts, keep):
                 raise ValueError(f"{name} must be a GLOBAL table of nb_cells entries")
             keep.append(a)
             setattr(d, name, a.ctypes.data)
-    for k in ("windows", "block", "max_ctas", "ring_cap", "retire_batch", "bank_cap",
+    for k in ("windows", "block", "max_ctas", "ring_cap", "retire_batch", "xs_global", "bank_cap",
               "inflight_limit"):
         setattr(d, k, int(opts.pop(k, 0) or 0))
     if opts:

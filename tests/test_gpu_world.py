@@ -75,6 +75,8 @@ CASES = {
     "absdom_ranks2": (configs.absorption_dominated(20_000), 2, dict(max_ctas=148)),
     "test_layer_ranks5": (configs.ref_test_layer(), 5, dict(max_ctas=32)),
     "hetero_8192_auto_windows": (configs.heterogeneous(8192, 256), 1, {}),
+    "hetero_8192_xs_global": (configs.heterogeneous(8192, 256), 1, dict(xs_global=1)),
+    "ranks3_xs_global": (configs.reference_default(20_000), 3, dict(max_ctas=148, xs_global=1)),
     "hetero_20000_ranks2": (configs.heterogeneous(20_000, 200), 2, dict(max_ctas=256)),
 }
 
