@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
   unsigned long long seed = 0;
   float x = 0.f, mu = 0.f, wmc = 0.f;
   float rmu = 0.f;  // recip_for_div(mu), refreshed whenever mu changes
+  int step = 1;     // dir_step(mu), likewise
   int idx = 0;
   bool active = false;
   bool exhausted = false;  // warp-uniform: the bank range has been handed out
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
           x = st.x;
           mu = st.y;
           rmu = recip_for_div(mu);
+          step = dir_step(mu);
           wmc = st.z;
           idx = __float_as_int(st.w);
           active = true;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
+      event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
                          p.xs, gacc, ncell, &p.ctr->acc_range);
       ++n_ev;
     }
@@ -474,9 +476,8 @@ __global__ void test_div_kernel(long long n, const float *a, const float *b, flo
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float r = recip_for_div(b[i]);
-    const unsigned ea = (__float_as_uint(a[i]) & 0x7fffffffu) - 0x0d800000u;
     float q = MCB_MAXREAL;
-    if (r != 0.0f && ea < 0x64000000u) q = div_by_recip(a[i], b[i], r);
+    if (r != 0.0f && fabsf(a[i]) >= 0x1p-100f && fabsf(a[i]) < 0x1p100f) q = div_by_recip(a[i], b[i], r);
     else if (b[i] < -MCB_EPS || MCB_EPS < b[i]) q = __fdiv_rn(a[i], b[i]);
     out[i] = q;
   }

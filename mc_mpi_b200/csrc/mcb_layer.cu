@@ -37,9 +37,11 @@ CellXs host_cell_xs(float sig, float a) {
   const float interaction_rate = (float)(1.0 - (double)a);
   const float sig_a = sig * a;
   const float sig_i = sig * interaction_rate;
-  // a float safely below 1/sig_i for the kernel's "certain crossing" test
-  const float inv_lb = sig_i > MCB_EPS ? (float)((1.0 / (double)sig_i) * (1.0 - 0x1p-20))
-                                       : std::numeric_limits<float>::infinity();
+  // a float safely below 1/sig_i for the kernel's "certain crossing" test: the whole margin of
+  // the test (2^-18, against <= 2^-22 of accumulated rounding) is taken here, once per cell
+  const float inv_lb = sig_i > MCB_EPS
+                           ? (float)((1.0 / (double)sig_i) * (1.0 - 0x1p-18 - 0x1p-19))
+                           : std::numeric_limits<float>::infinity();
   return make_float4(sig_a, sig_i, inv_lb, 0.0f);
 }
 

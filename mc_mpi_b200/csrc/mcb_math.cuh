@@ -12,7 +12,7 @@
 //    trajectory of a particle is the CPU trajectory bit for bit.  CUDA's own
 //    logf/expf (1 ulp, different polynomial) would not be.
 //    oracle/sweep_libm.c shows the restated algorithm == libm on every input
-//    the path can produce; tests/test_gpu_math.py shows device == libm.
+//    the path can produce; tests/test_gpu_primitives.py shows device == libm.
 //  * All float physics uses __f{add,sub,mul,div}_rn so nvcc can never contract
 //    a*b+c into an FMA (the reference build has none: no -march, SSE2 only).
 #pragma once
@@ -209,15 +209,13 @@ __device__ __forceinline__ float logf_glibc(float x, unsigned tb) {
 // glibc sysdeps/ieee754/flt-32/e_expf.c (EXP2F_TABLE_BITS 5).  Domain on the
 // path: -sig_a*di in [-inf, +0] (src/layer.cpp:175); the result only enters
 // as 1 - expf().
-__device__ __forceinline__ float expf_glibc_nonpos(float x, unsigned tb) {
+// the double-precision core: valid for x in [-104, 0] (finite); returns y with expf(x) = (float)y
+__device__ __forceinline__ double expf_core(float x, unsigned tb) {
   const double shift = c_mc.shift, inv_ln2_n = c_mc.inv_ln2_n;
   const double c0 = c_mc.c0, c1 = c_mc.c1, c2 = c_mc.c2;
-  const uint32_t ix = __float_as_uint(x);
-  // (double)x by re-biasing; +-0 and subnormals map to ~2^-896 instead, which
-  // gives the same 1.0f (expf of anything below 2^-126 in magnitude is 1.0f)
-  const uint32_t ax = ix & 0x7fffffffu;
-  const double xd = __hiloint2double(
-      (int)(((ax >> 3) + 0x38000000u) | (ix & 0x80000000u)), (int)(ix << 29));
+  // (double)x: one F2F on the (lightly used) conversion pipe; an integer re-bias would cost
+  // five issue slots of a kernel that is bound by instruction issue
+  const double xd = (double)x;
   const double z = __dmul_rn(inv_ln2_n, xd);
   double kd = __dadd_rn(z, shift);
   const uint32_t ki = (uint32_t)__double2loint(kd);
@@ -232,11 +230,18 @@ __device__ __forceinline__ float expf_glibc_nonpos(float x, unsigned tb) {
   const double r2 = __dmul_rn(r, r);
   double y = __fma_rn(c2, r, 1.0);
   y = __fma_rn(zz, r2, y);
-  y = __dmul_rn(y, s);
-  const float res = __double2float_rn(y);
-  // x < -103.97 underflows to +0 in glibc; covers -inf and garbage from the
-  // re-bias of huge |x|.  (1 - e) is 1.0f for every e <= 2^-25 anyway.)
+  return __dmul_rn(y, s);
+}
+__device__ __forceinline__ float expf_glibc_nonpos(float x, unsigned tb) {
+  const float res = __double2float_rn(expf_core(x, tb));
+  // x < -103.97 underflows to +0 in glibc; covers -inf and the garbage the core makes of huge |x|
   return (x > -104.0f) ? res : 0.0f;
+}
+// 1 - expf(x) as the event needs it (src/layer.cpp:175).  expf(x) <= 2^-25 gives exactly 1.0f
+// whatever its bits, so arguments below -104 (down to -inf, or NaN) are clamped instead of
+// tested: one FMNMX replaces a compare and a select
+__device__ __forceinline__ float one_minus_expf_nonpos(float x, unsigned tb) {
+  return __fsub_rn(1.0f, __double2float_rn(expf_core(fmaxf(x, -104.0f), tb)));
 }
 
 }  // namespace mcb

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   // particle state, include/types/particle.hpp:7-18, one history per lane
   unsigned long long seed = 0;
   float x = 0.f, mu = 0.f, wmc = 0.f, rmu = 0.f;
-  int idx = 0;
+  int idx = 0, step = 1;
   bool active = false;
   int cool = 0;        // iterations to wait before looking again for work that was not there
   unsigned n_ev = 0, n_sc = 0, n_it = 0;
@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         if (valid && (((side ? ok1 : ok0) >> lane) & 1u)) {
           slot_decode(a, b, d, seed, x, mu, wmc, idx);
           rmu = recip_for_div(mu);
+          step = dir_step(mu);
           active = true;
         }
         if (t0 | t1) {
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             }
             slot_decode(a, b, d, seed, x, mu, wmc, idx);
             rmu = recip_for_div(mu);
+          step = dir_step(mu);
             active = true;
           }
           if (lane == 0) atomicAdd(&sm->bank_pops, n);
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             seed = s_birth[w_off + r];
             mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
             rmu = recip_for_div(mu);
+          step = dir_step(mu);
             x = p.x_ini;
             wmc = p.wmc;
             idx = p.src_index;
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+      event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
                                 acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range);
       ++n_ev;
     }
