@@ -183,6 +183,14 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
       event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
                          p.xs, gacc, ncell, &p.ctr->acc_range);
       ++n_ev;
+      // a second event under the same vote for the lanes that are still live: the loop top
+      // (vote, count, branches) is shared by two events; a lane that finished on the first one
+      // waits one slot longer for its retirement
+      if ((wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)p.m)) {
+        event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+                                   acc_stride, p.xs, gacc, ncell, &p.ctr->acc_range);
+        ++n_ev;
+      }
     }
   }
 

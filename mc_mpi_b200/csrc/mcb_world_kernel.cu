@@ -567,8 +567,15 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
       event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
                                 acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range);
       ++n_ev;
+      // a second event under the same vote for the lanes that are still live: the loop top is
+      // shared by two events; a lane that finished on the first one waits one slot longer
+      if ((wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m)) {
+        event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+                                  acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range);
+        ++n_ev;
+      }
     }
-    ++n_it;   // lane slots offered to the event: n_ev / n_it = lane utilisation
+    n_it += 2;   // lane slots offered to the event: n_ev / n_it = lane utilisation
   }
 
   // ---- per-CTA flush: counters once, the CTA-private tally merged into the rank's
