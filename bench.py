@@ -350,8 +350,7 @@ def run_single_arm(args, dev):
 
         def e2e_step():
             # Layer.particles (host, 24-byte records) -> GPU -> weights_absorbed + counters back
-            _abi.check(_abi.lib().mcb200_layer_push(e_layer._h, host.data_ptr(), n_e2e))
-            c = e_layer.simulate(-1)
+            c = e_layer.simulate_host((host.data_ptr(), n_e2e))
             _abi.check(_abi.lib().mcb200_layer_weights_absorbed(e_layer._h, wa.ctypes.data))
             return c
 
@@ -368,8 +367,9 @@ def run_single_arm(args, dev):
                "h2d_bytes_per_step": n_e2e * PARTICLE_DTYPE.itemsize,
                "d2h_bytes_per_step": int(wa.nbytes + ctypes.sizeof(_abi.Counts)),
                "histories_per_step": n_e2e,
-               "interface": "mcb200_layer_push(host Particle[]) + mcb200_layer_simulate(-1) + "
-                            "mcb200_layer_weights_absorbed (what Layer::simulate / cusimulate do)"}
+               "interface": "mcb200_layer_simulate_host(host Particle[]) (chunked: the H2D copy of chunk "
+                            "k+1 under the tracking of chunk k) + mcb200_layer_weights_absorbed -- "
+                            "what Layer::simulate / cusimulate do"}
         e_layer.close()
     elif not args.no_e2e:
         # the public call sequence of a whole run: config scalars in, the tally back on the host

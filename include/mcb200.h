@@ -133,6 +133,14 @@ int mcb200_layer_push_device(mcb200_layer *l, const void *dev_aos, int64_t n);
 int mcb200_layer_simulate(mcb200_layer *l, int64_t nb_particles,
                           mcb200_counts *counts);
 
+/* The same for particles that sit in HOST memory, what Layer::simulate(.., use_gpu) /
+ * cusimulate do with `particles` (src/layer.cpp:257-263, src/culayer.cu:41-92): appends the n
+ * records and tracks exactly them, in chunks -- the host-to-device copy of chunk k+1 runs under
+ * the tracking of chunk k (pinned host memory makes the copies asynchronous; pageable memory
+ * works, without the overlap).  Equivalent to push(aos, n) + simulate(n). */
+int mcb200_layer_simulate_host(mcb200_layer *l, const mcb200_particle *aos, int64_t n,
+                               mcb200_counts *counts);
+
 /* ---- results ---------------------------------------------------------- */
 int mcb200_layer_counts(mcb200_layer *l, mcb200_counts *out);
 /* particles_left / particles_right (layer.hpp:94-95): copy up to `cap`
@@ -317,6 +325,9 @@ int mcb200_layer_weights_absorbed(mcb200_layer *l, float *out_m);
 int mcb200_layer_weights_absorbed_f64(mcb200_layer *l, double *out_m);
 int mcb200_layer_weights_absorbed_exact(mcb200_layer *l, uint32_t *out_4m,
                                         int32_t *lsb_log2);
+/* zero weights_absorbed and the class weights (the reference's callers do
+ * `std::fill(weights_absorbed...)` on the public vector between runs) */
+int mcb200_layer_reset_tally(mcb200_layer *l);
 /* Layer::dump_WA(), src/layer.cpp:363-380, same "%.4e %.3e\n" text; path NULL
  * -> "WA.out" in the current directory like the reference */
 int mcb200_layer_dump_WA(mcb200_layer *l, const char *path);
@@ -329,7 +340,8 @@ void *mcb200_layer_stream(mcb200_layer *l);
  *   "tally_mode"   0 auto, 1 CTA-private shared-memory tally, 2 global (L2) tally
  *   "block"        threads per CTA,  "blocks_per_sm" CTAs per SM
  *   "retire_batch" lanes of a warp without a live history before retire/refill runs (0 auto)
- *   "birth_chunk"  max particles born per launch */
+ *   "birth_chunk"  max particles born per launch
+ *   "host_chunk"   max particles per chunk of mcb200_layer_simulate_host */
 int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value);
 
 const char *mcb200_last_error(void);

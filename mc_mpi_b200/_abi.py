@@ -118,6 +118,8 @@ SYMBOLS = {
     "mcb200_layer_push": (C.c_int, [_P, _P, _I64]),
     "mcb200_layer_push_device": (C.c_int, [_P, _P, _I64]),
     "mcb200_layer_simulate": (C.c_int, [_P, _I64, C.POINTER(Counts)]),
+    "mcb200_layer_simulate_host": (C.c_int, [_P, _P, _I64, C.POINTER(Counts)]),
+    "mcb200_layer_reset_tally": (C.c_int, [_P]),
     "mcb200_layer_counts": (C.c_int, [_P, C.POINTER(Counts)]),
     "mcb200_layer_pop_left": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),
     "mcb200_layer_pop_right": (C.c_int, [_P, _P, _I64, C.POINTER(_I64)]),

@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <climits>
+#include <mutex>
 #include <utility>
+#include <vector>
 
 #include "../../include/mcb200/culayer.hpp"
 #include "../../include/mcb200/layer.hpp"
@@ -176,13 +179,21 @@ void Layer::simulate(int nb_particles, int /*nthread*/, bool /*use_gpu*/) {
     n_birth = nb_particles_create < want ? nb_particles_create : want;
   }
   const long long n_host = want - n_birth;
+  mcb200_counts c;
   if (n_host > 0) {
+    // the tail of `particles` (src/layer.cpp:319), copied in chunks under the tracking
     const Particle *tail = particles.data() + (particles.size() - (size_t)n_host);
-    die_on(mcb200_layer_push(h_, reinterpret_cast<const mcb200_particle *>(tail), n_host), "push");
+    die_on(mcb200_layer_simulate_host(h_, reinterpret_cast<const mcb200_particle *>(tail), n_host, &c),
+           "simulate_host");
     particles.resize(particles.size() - (size_t)n_host);
   }
-  mcb200_counts c;
-  die_on(mcb200_layer_simulate(h_, want, &c), "simulate");
+  if (n_birth > 0 || n_host == 0) die_on(mcb200_layer_simulate(h_, n_birth, &c), "simulate");
+  // the reference's counters are `int` (include/layer/layer.hpp:97,109): refuse to wrap
+  if (c.n_unborn > INT_MAX || c.nb_disabled > INT_MAX) {
+    std::fprintf(stderr, "Layer: more than INT_MAX particles in nb_disabled / nb_particles_create; "
+                         "use the C ABI (64-bit counters) for runs of this size\n");
+    std::exit(EXIT_FAILURE);
+  }
   nb_particles_create = (int)c.n_unborn;
   nb_disabled = (int)c.nb_disabled;
 
@@ -278,12 +289,28 @@ void cusimulate(int n, Particle *particles, float const *const sigs,
   d.right_border = 0;            // who does the border bookkeeping (layer.cpp:264-298)
   d.sigs = sigs;
   d.absorption_rates = absorption_rates;
-  mcb200_layer *h = nullptr;
-  die_on(mcb200_layer_create(&d, &h), "cusimulate: layer");
-  die_on(mcb200_layer_push(h, reinterpret_cast<const mcb200_particle *>(particles), n),
-         "cusimulate: push");
+  // one device layer is kept between calls (stream, events, tally, outboxes: nine
+  // allocations) and only rebuilt when the geometry changes; the reference allocates and frees
+  // its buffers per call (src/culayer.cu:57-92)
+  static std::mutex mu;
+  static mcb200_layer *cached = nullptr;
+  static mcb200_layer_desc cached_desc;
+  std::lock_guard<std::mutex> lock(mu);
+  const bool same = cached && cached_desc.device == d.device && cached_desc.index_start == d.index_start &&
+                    cached_desc.m == d.m && cached_desc.dx == d.dx;
+  if (!same) {
+    if (cached) mcb200_layer_destroy(cached);
+    cached = nullptr;
+    die_on(mcb200_layer_create(&d, &cached), "cusimulate: layer");
+    cached_desc = d;
+  } else {
+    die_on(mcb200_layer_set_cross_sections(cached, sigs, absorption_rates), "cusimulate: tables");
+    die_on(mcb200_layer_reset_tally(cached), "cusimulate: reset");
+  }
+  mcb200_layer *h = cached;
   mcb200_counts c;
-  die_on(mcb200_layer_simulate(h, -1, &c), "cusimulate: simulate");
+  die_on(mcb200_layer_simulate_host(h, reinterpret_cast<const mcb200_particle *>(particles), n, &c),
+         "cusimulate: simulate");
   int64_t nl = 0, nr = 0;
   mcb200_particle *out = reinterpret_cast<mcb200_particle *>(particles);
   die_on(mcb200_layer_pop_left(h, out, n, &nl), "cusimulate: pop_left");
@@ -296,5 +323,4 @@ void cusimulate(int n, Particle *particles, float const *const sigs,
   std::vector<float> w((size_t)n_cells);
   die_on(mcb200_layer_weights_absorbed(h, w.data()), "cusimulate: tally");
   for (int j = 0; j < n_cells; ++j) weights_absorbed[j] += w[(size_t)j];
-  mcb200_layer_destroy(h);
 }

@@ -133,6 +133,13 @@ struct mcb200_layer {
   unsigned long long *h_cls = nullptr;  // pinned: [2][3] halves of the 3 class accumulators
   void *d_stage = nullptr;            // AoS staging for push / pop
   long long stage_cap = 0;            // in particles
+  // pipelined host path (simulate_host): a copy stream and two staging buffers, so that the
+  // H2D copy of chunk k+1 runs under the tracking of chunk k
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  void *d_pipe[2] = {nullptr, nullptr};
+  long long pipe_cap = 0;             // particles per staging buffer
+  long long opt_host_chunk = 1ll << 25;
   bool xs_dirty = true;
   mcb::JumpTable seed_jump;
   // --- knobs / cumulative stats
@@ -566,6 +573,11 @@ void mcb200_layer_destroy(mcb200_layer *l) {
     cudaFree(l->d_acc);
     cudaFree(l->d_ctr);
     cudaFree(l->d_stage);
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(l->d_pipe[b]);
+      if (l->ev_copied[b]) cudaEventDestroy(l->ev_copied[b]);
+    }
+    if (l->copy_stream) cudaStreamDestroy(l->copy_stream);
     if (l->h_ctr) cudaFreeHost(l->h_ctr);
     if (l->h_cls) cudaFreeHost(l->h_cls);
     if (l->ev0) cudaEventDestroy(l->ev0);
@@ -719,6 +731,91 @@ int mcb200_layer_simulate(mcb200_layer *l, int64_t nb_particles, mcb200_counts *
     want -= take;
   }
   return fill_counts(l, counts);
+}
+
+int mcb200_layer_simulate_host(mcb200_layer *l, const mcb200_particle *aos, int64_t n,
+                               mcb200_counts *counts) {
+  if (!l || n < 0 || (n > 0 && !aos)) return fail(MCB200_ERR_INVALID, "simulate_host: bad argument");
+  DeviceGuard g(l->device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "simulate_host: cudaSetDevice failed");
+  if (l->peer[0].base || l->peer[1].base) {
+    // a connected neighbour's inbox bounds a launch: take the plain path
+    int rc = push_any(l, aos, false, n);
+    if (rc) return rc;
+    return mcb200_layer_simulate(l, n, counts);
+  }
+  // chunk sizes grow (x4 from 1M) up to `host_chunk`: only the first, small copy is exposed,
+  // every later one runs under the tracking of the chunk before it; few launches, because
+  // each one ends with a tail of its longest histories
+  const long long cmax = l->opt_host_chunk < l->opt_birth_chunk ? l->opt_host_chunk : l->opt_birth_chunk;
+  std::vector<long long> offs, cnts;
+  for (long long off = 0, c = (1ll << 20) < cmax ? (1ll << 20) : cmax; off < n;
+       c = c * 4 < cmax ? c * 4 : cmax) {
+    const long long cnt = (n - off) < c ? (n - off) : c;
+    offs.push_back(off);
+    cnts.push_back(cnt);
+    off += cnt;
+  }
+  const long long nchunks = (long long)offs.size();
+  if (n > 0) {
+    if (!l->copy_stream) {
+      MCB_CUDA(cudaStreamCreateWithFlags(&l->copy_stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) MCB_CUDA(cudaEventCreateWithFlags(&l->ev_copied[b], cudaEventDisableTiming));
+    }
+    long long need = 0;
+    for (long long c : cnts) need = c > need ? c : need;
+    if (l->pipe_cap < need) {
+      for (int b = 0; b < 2; ++b) {
+        cudaFree(l->d_pipe[b]);
+        l->d_pipe[b] = nullptr;
+      }
+      l->pipe_cap = 0;
+      for (int b = 0; b < 2; ++b)
+        MCB_CUDA(cudaMalloc(&l->d_pipe[b], (size_t)need * sizeof(mcb200_particle)));
+      l->pipe_cap = need;
+    }
+  }
+  auto copy_chunk = [&](long long k) -> int {
+    const int b = (int)(k & 1);
+    MCB_CUDA(cudaMemcpyAsync(l->d_pipe[b], aos + offs[(size_t)k],
+                             (size_t)cnts[(size_t)k] * sizeof(mcb200_particle),
+                             cudaMemcpyHostToDevice, l->copy_stream));
+    MCB_CUDA(cudaEventRecord(l->ev_copied[b], l->copy_stream));
+    return MCB200_OK;
+  };
+  if (nchunks > 0) {
+    int rc = copy_chunk(0);
+    if (rc) return rc;
+  }
+  for (long long k = 0; k < nchunks; ++k) {
+    const long long cnt = cnts[(size_t)k];
+    const int b = (int)(k & 1);
+    // the other staging buffer is free: track() of chunk k-1 synchronised the tracking stream
+    // after its transpose.  Its copy runs on the copy engine while chunk k is tracked.
+    if (k + 1 < nchunks) {
+      int rc = copy_chunk(k + 1);
+      if (rc) return rc;
+    }
+    int rc = soa_reserve(l, &l->bank, l->n_bank, l->n_bank + cnt);
+    if (rc) return rc;
+    MCB_CUDA(cudaStreamWaitEvent(l->stream, l->ev_copied[b], 0));
+    MCB_CUDA(mcb::launch_aos_to_soa(cnt, l->d_pipe[b], l->bank.seed + l->n_bank,
+                                    l->bank.st + l->n_bank, l->stream));
+    l->gpu_launches++;
+    l->n_bank += cnt;
+    rc = track(l, cnt);   // blocking: returns when chunk k is tracked
+    if (rc) return rc;
+  }
+  return fill_counts(l, counts);
+}
+
+int mcb200_layer_reset_tally(mcb200_layer *l) {
+  if (!l) return fail(MCB200_ERR_INVALID, "reset_tally: null layer");
+  DeviceGuard g(l->device);
+  MCB_CUDA(cudaMemsetAsync(l->d_acc, 0, l->acc_words() * sizeof(unsigned), l->stream));
+  MCB_CUDA(cudaStreamSynchronize(l->stream));
+  for (int k = 0; k < 3; ++k) l->w_cls[k] = 0.0;
+  return MCB200_OK;
 }
 
 int mcb200_layer_counts(mcb200_layer *l, mcb200_counts *out) {
@@ -941,7 +1038,10 @@ int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value) {
   else if (k == "block") l->opt_block = (int)value;
   else if (k == "blocks_per_sm") l->opt_bps = (int)value;
   else if (k == "retire_batch") l->opt_retire_batch = (int)value;
-  else if (k == "birth_chunk") {
+  else if (k == "host_chunk") {
+    if (value <= 0) return fail(MCB200_ERR_INVALID, "set_option: host_chunk must be positive");
+    l->opt_host_chunk = value;
+  } else if (k == "birth_chunk") {
     if (value <= 0) return fail(MCB200_ERR_INVALID, "set_option: birth_chunk must be positive");
     l->opt_birth_chunk = value;
   } else

@@ -103,6 +103,22 @@ class Layer:
     def push_device(self, dev_ptr: int, n: int):
         check(_abi.lib().mcb200_layer_push_device(self._h, C.c_void_p(dev_ptr), int(n)))
 
+    def simulate_host(self, particles) -> dict:
+        """track particles that sit in host memory (a numpy array of PARTICLE_DTYPE, or a
+        (pointer, count) pair for pinned buffers): chunked, the H2D copy of chunk k+1 under the
+        tracking of chunk k -- what Layer::simulate(.., use_gpu) does with `particles`"""
+        c = Counts()
+        if isinstance(particles, tuple):
+            ptr, n = particles
+        else:
+            p = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+            ptr, n = p.ctypes.data, len(p)
+        check(_abi.lib().mcb200_layer_simulate_host(self._h, C.c_void_p(ptr), int(n), C.byref(c)))
+        return c.as_dict()
+
+    def reset_tally(self):
+        check(_abi.lib().mcb200_layer_reset_tally(self._h))
+
     # -- the hot path --
     def simulate(self, nb_particles=-1) -> dict:
         """Layer::simulate, src/layer.cpp:239-361; -1 = until nothing is left."""

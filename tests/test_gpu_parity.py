@@ -336,3 +336,31 @@ def test_full_size_properties(gpu):
     o.simulate(-1, nthread=os.cpu_count() or 1)
     rel = np.abs(prof - o.tally_f64) / o.tally_f64
     assert rel.max() < 0.02 and rel.mean() < 0.004   # ~1/sqrt(histories per cell) noise
+
+
+def test_simulate_host_pipeline_equals_oracle(gpu, mcb_lib):
+    """mcb200_layer_simulate_host (host particles copied in chunks under the tracking of the
+    chunk before) gives what push + simulate gives: the oracle's result, bit for bit; the
+    tally can be zeroed between runs (mcb200_layer_reset_tally)."""
+    import ctypes as C
+    cfg = configs.reference_default(60_000)
+    o = make_oracle(cfg)
+    o.simulate(-1)
+    host = np.zeros(cfg.nb_particles, dtype=PARTICLE_DTYPE)
+    dx = np.float32(np.float32(cfg.x_max - cfg.x_min) / np.float32(cfg.nb_cells))
+    assert mcb_lib.mcb200_test_birth(0, cfg.x_ini, float(np.float32(1.0 / cfg.nb_particles)),
+                                     float(dx), cfg.nb_particles, 5127801, host.ctypes.data) == 0
+    with Layer(cfg.x_min, cfg.x_max, 0, cfg.nb_cells, cfg.particle_min_weight, keep_border=True) as g:
+        for rep in range(2):
+            # three chunk shapes: one chunk, several growing ones, a ragged tail
+            g.set_option("host_chunk", (1 << 25, 1 << 14)[rep])
+            g.simulate_host(host)
+            x, _ = g.weights_absorbed_exact()
+            assert np.array_equal(x, o.tally_exact)
+            left, right = g.pop_left(), g.pop_right()
+            assert particles_equal(left, np.concatenate([o.particles_left, o.absorbed_left]))
+            assert particles_equal(right, np.concatenate([o.particles_right, o.absorbed_right]))
+            g.reset_tally()
+            assert not g.weights_absorbed_f64.any()
+        c = g.counts()
+        assert c["events"] == 2 * o.stats()["events"] and c["nb_active"] == 0
