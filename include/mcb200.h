@@ -311,7 +311,8 @@ int mcb200_world_reset_tally(mcb200_world *w);
  * disjoint slices concatenated, nb_cells entries */
 int mcb200_world_gather_tally_f64(mcb200_world *const *worlds, int32_t n, double *out_nb_cells);
 /* knobs: "max_run_ms" (device-side cap on a run, 0 = none), "stall_ms" (the host stops a run
- * whose global counters have not moved for this long; default 15000) */
+ * whose global counters have not moved for this long; default 15000), "rng" (0 = LCG parity
+ * mode, 1 = Philox2x32-10, see mcb200_layer_set_option), "retire_batch", "inflight_limit" */
 int mcb200_world_set_option(mcb200_world *w, const char *key, int64_t value);
 void *mcb200_world_stream(mcb200_world *w);
 
@@ -340,6 +341,11 @@ void *mcb200_layer_stream(mcb200_layer *l);
  *   "tally_mode"   0 auto, 1 CTA-private shared-memory tally, 2 global (L2) tally
  *   "block"        threads per CTA,  "blocks_per_sm" CTAs per SM
  *   "retire_batch" lanes of a warp without a live history before retire/refill runs (0 auto)
+ *   "rng"          0 = the reference's per-particle LCG stream (src/random.cpp:12-16): results
+ *                  equal the CPU reference's bit for bit (the default, the parity mode);
+ *                  1 = counter-based Philox2x32-10 on (history id, event number), keyed by the
+ *                  seed given to create_particles: no seed chain, statistically equivalent
+ *                  results (tests/test_gpu_philox.py states the acceptance bounds)
  *   "birth_chunk"  max particles born per launch
  *   "host_chunk"   max particles per chunk of mcb200_layer_simulate_host */
 int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value);
@@ -353,6 +359,10 @@ int mcb200_device_count(void);
  * out[i] = the float (src/curandom.cu:7-14, checked like src/test_curandom.cu) */
 int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host,
                          int64_t n);
+/* Philox2x32-10 on the device (the "rng" = 1 generator): out[2i], out[2i+1] = the two output
+ * words for counter (c0[i], c1[i]) and key[i]; checked against Random123's known answers */
+int mcb200_test_philox(int device, const uint32_t *c0_host, const uint32_t *c1_host,
+                       const uint32_t *key_host, uint32_t *out2_host, int64_t n);
 /* device logf / expf as used by the tracking kernel, element-wise */
 int mcb200_test_logf(int device, const float *in_host, float *out_host, int64_t n);
 int mcb200_test_expf(int device, const float *in_host, float *out_host, int64_t n);

@@ -161,6 +161,7 @@ SYMBOLS = {
     "mcb200_abi_version": (C.c_int, []),
     "mcb200_device_count": (C.c_int, []),
     "mcb200_test_rnd_real": (C.c_int, [C.c_int, _P, _P, _I64]),
+    "mcb200_test_philox": (C.c_int, [C.c_int, _P, _P, _P, _P, _I64]),
     "mcb200_test_logf": (C.c_int, [C.c_int, _P, _P, _I64]),
     "mcb200_test_expf": (C.c_int, [C.c_int, _P, _P, _I64]),
     "mcb200_test_edge_distance": (C.c_int, [C.c_int, _P, _P, _P, _I64]),

@@ -43,6 +43,9 @@ double acc_to_double(const unsigned d[kAccDigits]);
 // out[4*c + j] for the first m cells
 void acc_halves_to_digits(const unsigned *raw, int ncell, int m, unsigned *out_4m);
 
+// the 32-bit Philox key of a run from the 64-bit seed the caller gave (src/layer.cpp:36)
+inline unsigned philox_key(unsigned long long seed) { return (unsigned)(seed ^ (seed >> 32)); }
+
 const char *last_error_cstr();
 void set_last_error(const std::string &m);
 std::string get_last_error();

@@ -38,7 +38,7 @@ struct TrackSmem {
 // events/s); the kernel is issue-bound with ~5 eligible warps per issue slot, so the extra
 // occupancy buys nothing.  The 1024-thread one exists for sub-slabs whose CTA-private tally
 // only fits once per SM.
-template <bool SHARED, int MAXB>
+template <bool SHARED, int MAXB, int RNG>
 __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const TrackParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem *sm = reinterpret_cast<TrackSmem *>(smem_raw);
@@ -180,15 +180,16 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) track_kernel(const 
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s, acc_stride,
-                         p.xs, gacc, ncell, &p.ctr->acc_range);
+      event_step<SHARED, SHARED, RNG>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+                                      acc_stride, p.xs, gacc, ncell, &p.ctr->acc_range, p.rng_key);
       ++n_ev;
       // a second event under the same vote for the lanes that are still live: the loop top
       // (vote, count, branches) is shared by two events; a lane that finished on the first one
       // waits one slot longer for its retirement
       if ((wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)p.m)) {
-        event_step<SHARED, SHARED>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
-                                   acc_stride, p.xs, gacc, ncell, &p.ctr->acc_range);
+        event_step<SHARED, SHARED, RNG>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s,
+                                        acc_s, acc_stride, p.xs, gacc, ncell, &p.ctr->acc_range,
+                                        p.rng_key);
         ++n_ev;
       }
     }
@@ -237,13 +238,17 @@ size_t track_smem_bytes(int tally_mode, int m) {
 }
 
 typedef void (*TrackFn)(const TrackParams);
-static TrackFn track_fn(int mode, int block) {
-  if (block <= 256) return mode == kTallyShared ? track_kernel<true, 256> : track_kernel<false, 256>;
-  return mode == kTallyShared ? track_kernel<true, 1024> : track_kernel<false, 1024>;
+static TrackFn track_fn(int mode, int block, int rng) {
+  if (rng == 0) {
+    if (block <= 256) return mode == kTallyShared ? track_kernel<true, 256, 0> : track_kernel<false, 256, 0>;
+    return mode == kTallyShared ? track_kernel<true, 1024, 0> : track_kernel<false, 1024, 0>;
+  }
+  if (block <= 256) return mode == kTallyShared ? track_kernel<true, 256, 1> : track_kernel<false, 256, 1>;
+  return mode == kTallyShared ? track_kernel<true, 1024, 1> : track_kernel<false, 1024, 1>;
 }
 
 cudaError_t track_configure(int device, int m, int want_mode, int want_block,
-                            int want_blocks_per_sm, TrackLaunch *out) {
+                            int want_blocks_per_sm, int rng, TrackLaunch *out) {
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return e;
@@ -272,13 +277,14 @@ cudaError_t track_configure(int device, int m, int want_mode, int want_block,
   }
   if (block > 1024 || block % 32) return cudaErrorInvalidValue;
 
+  out->rng = rng ? 1 : 0;
   out->tally_mode = mode;
   out->block = block;
   out->grid = prop.multiProcessorCount * bps;
   if (out->grid > kStripes) out->grid = kStripes;
   out->smem = smem;
-  return cudaFuncSetAttribute(track_fn(mode, block), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)smem);
+  return cudaFuncSetAttribute(track_fn(mode, block, out->rng),
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 int track_grid(const TrackLaunch &cfg, long long take) {
@@ -289,8 +295,8 @@ int track_grid(const TrackLaunch &cfg, long long take) {
 
 cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStream_t stream) {
   if (p.take_count <= 0) return cudaSuccess;
-  track_fn(cfg.tally_mode, cfg.block)<<<track_grid(cfg, p.take_count), cfg.block, cfg.smem,
-                                        stream>>>(p);
+  track_fn(cfg.tally_mode, cfg.block, cfg.rng)<<<track_grid(cfg, p.take_count), cfg.block, cfg.smem,
+                                                 stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -390,6 +396,46 @@ cudaError_t launch_birth(long long n, unsigned long long chain_state, const Jump
   const Affine stride = jump_map(seed_jump, (unsigned long long)grid * block);
   birth_kernel<<<grid, block, 0, stream>>>(n, chain_state, seed_jump, stride, x_ini, wmc, index,
                                            seed_out, st_out);
+  return cudaGetLastError();
+}
+
+// Philox mode: no chain -- history `first_id + i` IS its counter; event 0 draws the direction
+__global__ void __launch_bounds__(256) birth_philox_kernel(long long n, unsigned long long first_id,
+                                                           unsigned key, float x_ini, float wmc,
+                                                           int index,
+                                                           unsigned long long *__restrict__ seed_out,
+                                                           float4 *__restrict__ st_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long c0 = (first_id + (unsigned long long)i) << kPhiloxEventBits;
+    const uint2 w = philox_draws(c0, key);
+    const float mu = __fsub_rn(__fmul_rn(2.0f, u32_to_real(w.x)), 1.0f);
+    __stcs(&seed_out[i], c0 + 1ull);
+    __stcs(&st_out[i], make_float4(x_ini, mu, wmc, __int_as_float(index)));
+  }
+}
+
+cudaError_t launch_birth_philox(long long n, unsigned long long first_id, unsigned key, float x_ini,
+                                float wmc, int index, unsigned long long *seed_out, float4 *st_out,
+                                cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int block = 256;
+  long long want = (n + block - 1) / block;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  birth_philox_kernel<<<grid, block, 0, stream>>>(n, first_id, key, x_ini, wmc, index, seed_out, st_out);
+  return cudaGetLastError();
+}
+
+__global__ void test_philox_kernel(long long n, const unsigned *c0, const unsigned *c1,
+                                   const unsigned *key, uint2 *out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = philox2x32_10(c0[i], c1[i], key[i]);
+}
+cudaError_t launch_test_philox(long long n, const unsigned *c0, const unsigned *c1,
+                               const unsigned *key, uint2 *out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  test_philox_kernel<<<(int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, stream>>>(n, c0, c1, key, out);
   return cudaGetLastError();
 }
 

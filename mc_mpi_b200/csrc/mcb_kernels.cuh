@@ -82,12 +82,14 @@ struct TrackParams {
   int write_side[2];     // 0: global border, escapees are only counted
   int retire_batch;      // retire / refill once this many lanes of a warp are without a live
                          // history (>= 1): amortises the bookkeeping over short segments
+  unsigned rng_key;      // Philox key (rng mode 1)
   DevCounters *ctr;
 };
 
 enum TallyMode { kTallyShared = 1, kTallyGlobal = 2 };
 
 struct TrackLaunch {
+  int rng;          // 0 = LCG (parity mode), 1 = Philox2x32-10
   int tally_mode;   // TallyMode
   int block;        // threads per CTA
   int grid;         // CTAs
@@ -96,7 +98,7 @@ struct TrackLaunch {
 
 size_t track_smem_bytes(int tally_mode, int m);
 cudaError_t track_configure(int device, int m, int want_mode, int want_block,
-                            int want_blocks_per_sm, TrackLaunch *out);
+                            int want_blocks_per_sm, int rng, TrackLaunch *out);
 // grid actually used for `take` particles (<= cfg.grid <= kStripes)
 int track_grid(const TrackLaunch &cfg, long long take);
 cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg,
@@ -122,6 +124,15 @@ cudaError_t launch_birth(long long n, unsigned long long chain_state,
                          const JumpTable &seed_jump, float x_ini, float wmc,
                          int index, unsigned long long *seed_out, float4 *st_out,
                          cudaStream_t stream);
+// Philox mode: history first_id + i starts at counter (first_id + i) << kPhiloxEventBits; its
+// event 0 is the birth (mu from word 0), so it is banked with event number 1
+cudaError_t launch_birth_philox(long long n, unsigned long long first_id, unsigned key,
+                                float x_ini, float wmc, int index,
+                                unsigned long long *seed_out, float4 *st_out,
+                                cudaStream_t stream);
+// known-answer-test: out[i] = philox2x32_10(c0[i], c1[i], key[i])
+cudaError_t launch_test_philox(long long n, const unsigned *c0, const unsigned *c1,
+                               const unsigned *key, uint2 *out, cudaStream_t stream);
 
 // 24-byte AoS records (include/types/particle.hpp) <-> bank layout
 cudaError_t launch_aos_to_soa(long long n, const void *aos,

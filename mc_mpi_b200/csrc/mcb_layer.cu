@@ -144,6 +144,8 @@ struct mcb200_layer {
   mcb::JumpTable seed_jump;
   // --- knobs / cumulative stats
   int opt_tally_mode = 0, opt_block = 0, opt_bps = 0, opt_retire_batch = 0;
+  int opt_rng = 0;                    // 0 = LCG (parity), 1 = Philox2x32-10
+  unsigned long long philox_next_id = 0;   // histories handed out so far in Philox mode
   long long opt_birth_chunk = 1ll << 26;
   bool cfg_dirty = true;
   mcb::TrackLaunch cfg{};
@@ -258,10 +260,18 @@ int birth(mcb200_layer *l, long long n) {
   if (rc) return rc;
   const float cell = l->x_ini / l->dx;  // :106, ignores x_min
   const int index = (int)cell;
-  MCB_CUDA(mcb::launch_birth(n, l->chain_state, l->seed_jump, l->x_ini, l->wmc, index,
-                             l->bank.seed + l->n_bank, l->bank.st + l->n_bank, l->stream));
+  if (l->opt_rng == 0) {
+    MCB_CUDA(mcb::launch_birth(n, l->chain_state, l->seed_jump, l->x_ini, l->wmc, index,
+                               l->bank.seed + l->n_bank, l->bank.st + l->n_bank, l->stream));
+    l->chain_state = mcb::jump_state(l->seed_jump, (unsigned long long)n, l->chain_state);
+  } else {
+    // counter-based: the seed given to create_particles is the KEY, history ids just count up
+    MCB_CUDA(mcb::launch_birth_philox(n, l->philox_next_id, mcb::philox_key(l->chain_state), l->x_ini,
+                                      l->wmc, index, l->bank.seed + l->n_bank,
+                                      l->bank.st + l->n_bank, l->stream));
+    l->philox_next_id += (unsigned long long)n;
+  }
   l->gpu_launches++;
-  l->chain_state = mcb::jump_state(l->seed_jump, (unsigned long long)n, l->chain_state);
   l->n_bank += n;
   l->n_unborn -= n;
   return MCB200_OK;
@@ -275,7 +285,7 @@ int track(mcb200_layer *l, long long take) {
   }
   if (l->cfg_dirty) {
     MCB_CUDA(mcb::track_configure(l->device, l->m, l->opt_tally_mode, l->opt_block, l->opt_bps,
-                                  &l->cfg));
+                                  l->opt_rng, &l->cfg));
     l->cfg_dirty = false;
   }
   const bool write_side[2] = {!l->left_border || l->keep_border,
@@ -336,6 +346,7 @@ int track(mcb200_layer *l, long long take) {
     }
   }
   p.ctr = l->d_ctr;
+  p.rng_key = mcb::philox_key(l->chain_state);
   // short segments (thin sub-slabs of a multi-GPU run) retire often: batch the bookkeeping
   p.retire_batch = l->opt_retire_batch > 0 ? l->opt_retire_batch : (l->m < 512 ? 4 : 2);
   if (p.retire_batch > 32) p.retire_batch = 32;
@@ -650,6 +661,8 @@ int mcb200_layer_clone(mcb200_layer *src, mcb200_layer **out) {
   l->opt_bps = src->opt_bps;
   l->opt_retire_batch = src->opt_retire_batch;
   l->opt_birth_chunk = src->opt_birth_chunk;
+  l->opt_rng = src->opt_rng;
+  l->philox_next_id = src->philox_next_id;
   l->events = src->events;
   l->scatters = src->scatters;
   for (int k = 0; k < 3; ++k) {
@@ -1038,7 +1051,12 @@ int mcb200_layer_set_option(mcb200_layer *l, const char *key, int64_t value) {
   else if (k == "block") l->opt_block = (int)value;
   else if (k == "blocks_per_sm") l->opt_bps = (int)value;
   else if (k == "retire_batch") l->opt_retire_batch = (int)value;
-  else if (k == "host_chunk") {
+  else if (k == "rng") {
+    if (value != 0 && value != 1) return fail(MCB200_ERR_INVALID, "set_option: rng is 0 (LCG) or 1 (Philox)");
+    if (l->n_bank > 0) return fail(MCB200_ERR_INVALID, "set_option: rng cannot change while particles are banked");
+    l->opt_rng = (int)value;
+    l->cfg_dirty = true;
+  } else if (k == "host_chunk") {
     if (value <= 0) return fail(MCB200_ERR_INVALID, "set_option: host_chunk must be positive");
     l->opt_host_chunk = value;
   } else if (k == "birth_chunk") {
@@ -1066,6 +1084,27 @@ int mcb200_test_rnd_real(int device, uint64_t *seeds_host, float *out_host, int6
   MCB_CUDA(mcb::launch_test_rnd_real(n, ds.p, dout.p, nullptr));
   MCB_CUDA(cudaMemcpy(seeds_host, ds.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
   MCB_CUDA(cudaMemcpy(out_host, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return MCB200_OK;
+}
+
+int mcb200_test_philox(int device, const uint32_t *c0_host, const uint32_t *c1_host,
+                       const uint32_t *key_host, uint32_t *out2_host, int64_t n) {
+  if (n < 0 || (n > 0 && (!c0_host || !c1_host || !key_host || !out2_host)))
+    return fail(MCB200_ERR_INVALID, "test_philox: bad argument");
+  if (n == 0) return MCB200_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MCB200_ERR_CUDA, "test_philox: cudaSetDevice failed");
+  DevScratch<unsigned> d0, d1, dk;
+  DevScratch<uint2> dout;
+  MCB_CUDA(d0.alloc((size_t)n));
+  MCB_CUDA(d1.alloc((size_t)n));
+  MCB_CUDA(dk.alloc((size_t)n));
+  MCB_CUDA(dout.alloc((size_t)n));
+  MCB_CUDA(cudaMemcpy(d0.p, c0_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(cudaMemcpy(d1.p, c1_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(cudaMemcpy(dk.p, key_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  MCB_CUDA(mcb::launch_test_philox(n, d0.p, d1.p, dk.p, dout.p, nullptr));
+  MCB_CUDA(cudaMemcpy(out2_host, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return MCB200_OK;
 }
 

@@ -138,6 +138,37 @@ __device__ __forceinline__ float lcg_to_real(uint64_t s) {
   return __fmul_rn(__ull2float_rn(s), 0x1p-63f);
 }
 
+// ---- Philox2x32-10: the counter-based "performance mode" generator ---------------------
+// (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123's
+// philox2x32_10: multiplier 0xD256D193, Weyl key bump 0x9E3779B9, 10 rounds -- pinned to its
+// known-answer vectors by tests/test_gpu_primitives.py.)  A particle's 64-bit `seed` field is
+// the COUNTER: history id << 23 | event number; the key is the run's seed.  One call per
+// event gives both draws an event can consume: word 0 -> the free-flight draw h, word 1 ->
+// the scattering angle.  No seed chain, no state to advance but the event number: any
+// event of any history can be recomputed from (id, event, key) alone.  The floats are formed
+// like rnd_real forms them (src/random.cpp:13-15): integer -> float, round to nearest, times a
+// power of two -- so h lies in [0, 1] inclusive here too.
+constexpr uint32_t kPhiloxM = 0xD256D193u;
+constexpr uint32_t kPhiloxW = 0x9E3779B9u;
+constexpr int kPhiloxEventBits = 23;   // events per history before the counter runs into the id
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi = __umulhi(kPhiloxM, c0);
+    const uint32_t lo = kPhiloxM * c0;
+    c0 = hi ^ key ^ c1;
+    c1 = lo;
+    key += kPhiloxW;
+  }
+  return make_uint2(c0, c1);
+}
+__device__ __forceinline__ uint2 philox_draws(uint64_t counter, uint32_t key) {
+  return philox2x32_10((uint32_t)counter, (uint32_t)(counter >> 32), key);
+}
+__device__ __forceinline__ float u32_to_real(uint32_t w) {
+  return __fmul_rn(__uint2float_rn(w), 0x1p-32f);
+}
+
 // affine map s -> a*s + c (mod 2^63); powers of the LCG step are such maps
 struct Affine {
   uint64_t a, c;

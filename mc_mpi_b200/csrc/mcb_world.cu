@@ -38,6 +38,7 @@ struct mcb200_world {
   unsigned long long inflight_limit = 0;
   int retire_batch = 0;
   long long max_run_ms = 0, stall_ms = 15000;
+  int rng = 0;                // 0 = LCG (parity mode), 1 = Philox2x32-10
   // --- device state
   cudaStream_t stream = nullptr, side = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -630,6 +631,8 @@ int mcb200_world_launch(mcb200_world *w) {
   p.src_index = w->src_index;
   p.src_total = p.src_window >= 0 ? (unsigned long long)w->nb_particles : 0ull;
   p.chain_state = w->seed0;
+  p.rng = w->rng;
+  p.rng_key = mcb::philox_key(w->seed0);
   p.x_ini = w->x_ini;
   p.wmc = (float)(1.0 / (double)w->nb_particles);   // src/layer.cpp:38
   p.inflight_limit = w->inflight_limit;
@@ -859,6 +862,7 @@ int mcb200_world_set_option(mcb200_world *w, const char *key, int64_t value) {
   const std::string k(key);
   if (k == "max_run_ms") w->max_run_ms = value;
   else if (k == "stall_ms") w->stall_ms = value;
+  else if (k == "rng" && (value == 0 || value == 1)) w->rng = (int)value;
   else if (k == "retire_batch") w->retire_batch = value < 1 ? 1 : value > 32 ? 32 : (int)value;
   else if (k == "inflight_limit" && value > 0) w->inflight_limit = (unsigned long long)value;
   else return fail(MCB200_ERR_INVALID, "world_set_option: unknown key " + k);

@@ -103,6 +103,8 @@ struct WorldParams {
   int src_index;                     // (int)(x_ini / dx), src/layer.cpp:106
   unsigned long long src_total;
   unsigned long long chain_state;    // Layer::seed before the first birth (src/layer.cpp:36)
+  int rng;                           // 0 = LCG (parity mode), 1 = Philox2x32-10
+  unsigned rng_key;                  // Philox key of the run
   float x_ini, wmc;
   unsigned long long inflight_limit; // births stop while born - disabled exceeds this
   // termination

@@ -142,7 +142,7 @@ __device__ __forceinline__ void note_disabled(WorldSmem *sm, const WorldParams &
 // XS_SMEM: the window's cell constants sit next to its tally in shared memory (false: they
 // are read from global memory / L2, which halves the shared memory a cell costs -- the shape
 // chosen for sub-slabs of ~1e6 cells)
-template <int MAXB, bool XS_SMEM>
+template <int MAXB, bool XS_SMEM, int RNG>
 __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const WorldParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WorldSmem *sm = reinterpret_cast<WorldSmem *>(smem_raw);
@@ -437,10 +437,16 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             if (base >= p.src_total) {
               if (lane == 0) wx->src_done = 1u;
             } else {
-              const unsigned long long s = jump_state(c_seed_jump, base + 1ull + (unsigned)lane,
-                                                      p.chain_state);
-              s_birth[lane] = lcg_next(s);                                   // :112 draw #1
-              s_birth[lane + 32] = lcg_next(affine_apply(c_seed_jump.pow2[5], s));
+              if (RNG == 0) {
+                const unsigned long long s = jump_state(c_seed_jump, base + 1ull + (unsigned)lane,
+                                                        p.chain_state);
+                s_birth[lane] = lcg_next(s);                                   // :112 draw #1
+                s_birth[lane + 32] = lcg_next(affine_apply(c_seed_jump.pow2[5], s));
+              } else {
+                // counter-based: history `base + j` is its own counter, event 0 = the birth
+                s_birth[lane] = (base + (unsigned)lane) << kPhiloxEventBits;
+                s_birth[lane + 32] = (base + 32ull + (unsigned)lane) << kPhiloxEventBits;
+              }
               __syncwarp();
               w_off = 0u;
               w_cnt = base + kWorkChunk <= p.src_total ? (unsigned)kWorkChunk
@@ -455,7 +461,12 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           const unsigned r = (unsigned)__popc(im & lt_mask);
           if (!active && r < n) {
             seed = s_birth[w_off + r];
-            mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
+            if (RNG == 0) {
+              mu = __fsub_rn(__fmul_rn(2.0f, lcg_to_real(seed)), 1.0f);
+            } else {
+              mu = __fsub_rn(__fmul_rn(2.0f, u32_to_real(philox_draws(seed, p.rng_key).x)), 1.0f);
+              seed += 1ull;
+            }
             rmu = recip_for_div(mu);
           step = dir_step(mu);
             x = p.x_ini;
@@ -564,14 +575,14 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
-      event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
-                                acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range);
+      event_step<XS_SMEM, true, RNG>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+                                acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range, p.rng_key);
       ++n_ev;
       // a second event under the same vote for the lanes that are still live: the loop top is
       // shared by two events; a lane that finished on the first one waits one slot longer
       if ((wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m)) {
-        event_step<XS_SMEM, true>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
-                                  acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range);
+        event_step<XS_SMEM, true, RNG>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
+                                  acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range, p.rng_key);
         ++n_ev;
       }
     }
@@ -651,9 +662,13 @@ size_t world_smem_bytes(int m_max, int block, bool xs_smem) {
 }
 
 typedef void (*WorldFn)(const WorldParams);
-static WorldFn world_fn(int block, bool xs_smem) {
-  if (block <= 256) return xs_smem ? world_kernel<256, true> : world_kernel<256, false>;
-  return xs_smem ? world_kernel<1024, true> : world_kernel<1024, false>;
+static WorldFn world_fn(int block, bool xs_smem, int rng) {
+  if (rng == 0) {
+    if (block <= 256) return xs_smem ? world_kernel<256, true, 0> : world_kernel<256, false, 0>;
+    return xs_smem ? world_kernel<1024, true, 0> : world_kernel<1024, false, 0>;
+  }
+  if (block <= 256) return xs_smem ? world_kernel<256, true, 1> : world_kernel<256, false, 1>;
+  return xs_smem ? world_kernel<1024, true, 1> : world_kernel<1024, false, 1>;
 }
 
 cudaError_t world_configure(int device, int m_max, int block, bool xs_smem, WorldLaunch *out,
@@ -664,12 +679,17 @@ cudaError_t world_configure(int device, int m_max, int block, bool xs_smem, Worl
   const size_t smem = world_smem_bytes(m_max, block, xs_smem);
   if (smem > prop.sharedMemPerBlockOptin || block % 32 || block > 1024 || block < 32)
     return cudaErrorInvalidValue;
-  e = cudaFuncSetAttribute(world_fn(block, xs_smem), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
+  for (int rng = 0; rng < 2; ++rng) {
+    e = cudaFuncSetAttribute(world_fn(block, xs_smem, rng),
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = 0, per_sm1 = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, world_fn(block, xs_smem, 0), block, smem);
   if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, world_fn(block, xs_smem), block, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, world_fn(block, xs_smem, 1), block, smem);
   if (e != cudaSuccess) return e;
+  if (per_sm1 < per_sm) per_sm = per_sm1;   // the launch shape must hold for both generators
   if (per_sm < 1) return cudaErrorInvalidValue;
   out->block = block;
   out->grid = prop.multiProcessorCount * per_sm;   // every CTA resident: the kernel is persistent
@@ -684,8 +704,8 @@ cudaError_t world_upload_jump_table(const JumpTable &jt) {
 }
 
 cudaError_t launch_world(const WorldParams &p, const WorldLaunch &cfg, cudaStream_t stream) {
-  world_fn(cfg.block, cfg.xs_smem != 0)<<<dim3((unsigned)p.cpw, (unsigned)p.V), cfg.block, cfg.smem,
-                                          stream>>>(p);
+  world_fn(cfg.block, cfg.xs_smem != 0, p.rng)<<<dim3((unsigned)p.cpw, (unsigned)p.V), cfg.block,
+                                                 cfg.smem, stream>>>(p);
   return cudaGetLastError();
 }
 
