@@ -97,6 +97,16 @@ def dump_weights_absorbed(path: str, weights: np.ndarray, cuts, dx: np.float32) 
             f.write(f"{proc}, {float(dx) * (i + 0.5):.18e}, {float(w32[i] / dx):.18e}\n")
 
 
+def dump_WA(path: str, weights: np.ndarray, dx: np.float32, x_min: float = 0.0) -> None:
+    """Layer::dump_WA (src/layer.cpp:363-380): "%.4e %.3e" of the cell centre and tally / dx,
+    in the reference's float arithmetic."""
+    w32 = weights.astype(np.float32)
+    with open(path, "w") as f:
+        for i in range(len(w32)):
+            x_mid = np.float32(np.float32(x_min) + np.float32(i) * dx) + 0.5 * float(dx)
+            f.write("%.4e %.3e\n" % (float(x_mid), float(np.float32(w32[i] / dx))))
+
+
 def dump_stats(path: str, rows_by_rank) -> None:
     """Worker::write_file (src/worker.cpp:63-181) with Timer::State's formats (src/timer.cpp:41-53):
     `rank, starttime, endtime, time_comp, time_send, time_recv, time_idle, nb_cycles, ` -- one row
@@ -149,48 +159,62 @@ def main(argv=None) -> int:
                                  sigs=cfg.sigs, absorption_rates=cfg.absorption_rates)
         torch.cuda.synchronize()
         t0, w0 = time.perf_counter(), time.time()
-        layer.simulate(-1)                      # Worker::spin
+        c = layer.simulate(-1)                  # Worker::spin
         elapsed = time.perf_counter() - t0
         weights, cuts, lay0 = layer.weights_absorbed_f64, [0, cfg.nb_cells], layer
-        stat_rows = [[(w0, w0 + elapsed, elapsed, 0.0, 0.0, 0.0, 1)]]
+        # phase timers (src/timer.cpp:57-102): Computation = device time of the tracking kernels
+        # (CUDA events), Idle = the rest of the wall time (launch gaps, read-back); no exchange
+        comp = min(c["track_ms"] * 1e-3, elapsed)
+        stat_rows = [[(w0, w0 + elapsed, comp, 0.0, 0.0, elapsed - comp, c["launches"])]]
     else:
         import torch.distributed as dist
 
-        from .world import SlabWorld, balanced_cuts
+        from .worker import Worker, occupancy
+        from .world import balanced_cuts
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        sw = SlabWorld(cfg, device=local, nb_particles_per_cycle=opt["nb_particles_per_cycle"],
-                       ramp_from=min(1 << 20, opt["nb_particles_per_cycle"]), transport="p2p",
-                       statistics_cycle_time=opt["statistics_cycle_time"] or 1e30)
+        # one persistent kernel per GPU for the whole run (csrc/mcb_world*.cu): the escapee
+        # exchange and the termination count happen on the device
+        wk = Worker(cfg, device=local)
         if opt["balance"]:
-            # a short pilot run places the cuts where the measured tracking time balances
-            pilot = cfg.with_particles(max(min(cfg.nb_particles // 20, 5_000_000), 1000))
-            pw = SlabWorld(pilot, device=local, nb_particles_per_cycle=opt["nb_particles_per_cycle"])
-            pw.spin()
-            t = torch.zeros(world, dtype=torch.float64, device="cuda")
-            t[rank] = pw.layer.counts()["track_ms"]
-            dist.all_reduce(t)
-            pw.layer.close()
-            sw.recut(balanced_cuts(sw.cuts, t.tolist(), cfg.nb_cells))
+            # a short pilot run places the cuts where the measured lane occupancy balances
+            pilot = max(min(cfg.nb_particles // 20, 20_000_000), 1000)
+            r = wk.spin(pilot)
+            cost = [row[0] for row in wk.all_ranks([occupancy(r)], "table")]
+            equal = [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world) for k in range(world + 1)]
+            wk.recut(balanced_cuts(equal, cost, cfg.nb_cells))
         dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        sw.spin()                               # Worker::spin
+        t0, w0 = time.perf_counter(), time.time()
+        r = wk.spin()                           # Worker::spin
         dist.barrier()
         elapsed = time.perf_counter() - t0
-        weights, cuts, lay0 = sw.gather_weights_absorbed(), sw.cuts, sw.layer
-        stat_rows = sw.gather_stat_rows()
+        weights = wk.gather_weights_absorbed()
+        cuts = wk.cuts or [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world)
+                           for k in range(world + 1)]
+        # phase timers from the DEVICE: the kernel's run time (CUDA events) splits into the time
+        # its lanes carried a history (Computation; the escapee stores into the neighbour GPU --
+        # the reference's Send -- are instructions of that kernel, the receive is a load from
+        # local memory: both 0 here) and the time they waited for neighbours / the end (Idle)
+        kern = r["kernel_ms"] * 1e-3
+        busy = kern * occupancy(r)
+        rows = wk.all_ranks([w0, w0 + elapsed, busy, 0.0, 0.0, max(elapsed - busy, 0.0), 1], "table")
+        stat_rows = [[tuple(row)] for row in rows]
+        lay0 = None
     if rank == 0:
         print(f"{elapsed:f}")                   # main.cpp:91
         os.makedirs("out", exist_ok=True)       # Worker::dump, src/worker.cpp:36-61
         dump_config(os.path.join("out", "config.yaml"), opt, world)
         dump_weights_absorbed(os.path.join("out", "weights.csv"), weights, cuts, dx)
         dump_stats(os.path.join("out", "stats.csv"), stat_rows)
-        lay0.dump_WA("WA.out")
+        if lay0 is not None:
+            lay0.dump_WA("WA.out")
+        else:
+            dump_WA("WA.out", weights[cuts[0]:cuts[1]], dx)   # rank 0's slice, src/layer.cpp:363-380
     if world > 1:
         import torch.distributed as dist
-        sw.close()          # unmap the neighbours' inboxes before anybody frees one
+        wk.close()          # unmap the neighbours' exchange blocks before anybody frees one
         dist.barrier()
         dist.destroy_process_group()
     return 0

@@ -53,6 +53,10 @@ def build_ref() -> str | None:
     and no prebuilt library travelled with the repo."""
     if reference_sources_present():
         _make("ref")
+        try:   # the reference's own GPU prototype for sm_100a (a courtesy baseline, bench.py)
+            _make("proto")
+        except Exception:
+            pass
     return REF_SO if os.path.isfile(REF_SO) else None
 
 

@@ -82,6 +82,7 @@ def test_driver_single_rank_flow_with_a_stand_in_layer(tmp_path, monkeypatch):
 
         def simulate(self, n):
             self.o.simulate(n)
+            return {"track_ms": 0.0, "launches": 1}   # the counters main() reads (Layer.simulate)
 
         @property
         def weights_absorbed_f64(self):
@@ -138,3 +139,44 @@ def test_driver_end_to_end(gpu, tmp_path):
     want = (o.tally_exact_f64.astype(np.float32) / dx).astype(np.float64)
     assert np.array_equal(got[:, 2], want)
     assert np.allclose(got[:, 1], float(dx) * (np.arange(1000) + 0.5), rtol=0, atol=1e-15)
+    # phase timers of the native driver (Worker::write_file format, src/worker.cpp:63-181):
+    # Computation is the DEVICE time of the tracking kernels (CUDA events), Idle the rest
+    rows = (tmp_path / "out" / "stats.csv").read_text().splitlines()
+    assert rows[0].startswith("rank, starttime, endtime, time_comp, time_send, time_recv, time_idle, nb_cycles")
+    f = [v.strip() for v in rows[1].split(",")]
+    start, end, comp, send, recv, idle, cycles = (float(v) for v in f[1:8])
+    assert int(f[0]) == 0 and end > start
+    assert 0.0 < comp <= (end - start) + 1e-6 and send == 0.0 and recv == 0.0
+    assert abs((comp + idle) - (end - start)) < 1e-3 and cycles >= 1
+    assert comp > 1e-4                      # 5.8e7 events take >= 0.2 ms of kernel time on a B200
+
+
+@pytest.mark.gpu
+def test_driver_two_ranks_device_timers(gpu, mcb_lib, tmp_path):
+    """2 ranks (needs 2 GPUs): the persistent-kernel driver writes one stats row per rank whose
+    Computation + Idle come from the device (kernel run time x lane occupancy / the rest), and the
+    weights equal the single-layer oracle's."""
+    if mcb_lib.mcb200_device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    sys.path.insert(0, HERE)
+    from mc_mpi_b200 import configs
+    from util import make_oracle
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", "-m", "mc_mpi_b200.main", CONFIG, "nvl"]
+    res = subprocess.run(cmd, cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    rows = (tmp_path / "out" / "stats.csv").read_text().splitlines()
+    assert len(rows) == 3
+    for r, row in enumerate(rows[1:]):
+        f = [v.strip() for v in row.split(",")]
+        start, end, comp, send, recv, idle = (float(v) for v in f[1:7])
+        assert int(f[0]) == r and comp > 0 and idle >= 0 and comp <= (end - start) + 1e-6
+    got = np.loadtxt(tmp_path / "out" / "weights.csv", delimiter=",", skiprows=1)
+    o = make_oracle(configs.reference_default(100_000))
+    o.simulate(-1, nthread=os.cpu_count() or 1)
+    dx = np.float32(o.dx)
+    want = (o.tally_exact_f64.astype(np.float32) / dx).astype(np.float64)
+    assert np.array_equal(got[:, 2], want)
+    assert sorted(set(got[:, 0])) == [0.0, 1.0]
