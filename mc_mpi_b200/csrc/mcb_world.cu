@@ -480,6 +480,8 @@ int mcb200_world_create(const mcb200_world_desc *d, mcb200_world **out) {
     unsigned c = pow2_floor((512ull << 20) / (24ull * (unsigned long long)w->cfg.grid));
     w->bank_cap = c < 1024 ? 1024 : c > (1u << 20) ? (1u << 20) : c;
   }
+  if (w->bank_cap < 4u * (unsigned)w->cfg.block)
+    return bail(fail(MCB200_ERR_INVALID, "world_create: bank_cap must be at least 4 x the CTA size"));
   w->bank_log2 = ilog2(w->bank_cap);
   w->retire_batch = d->retire_batch > 0 ? (d->retire_batch > 32 ? 32 : d->retire_batch)
                                         : (m_max_all / w->V < 256 ? 6 : m_max_all / w->V < 512 ? 4 : 2);
@@ -753,7 +755,9 @@ int mcb200_world_wait(mcb200_world *w, mcb200_world_result *out) {
                                "time, or a rank was prepared while a neighbour's previous run was still "
                                "ending)"
                              : "world_wait: the kernel hit the max_run_ms cap and stopped itself");
-  if (err == MCB200_ERR_CAPACITY) return fail(err, "world_wait: a window's bank overflowed (raise bank_cap)");
+  if (err == MCB200_ERR_CAPACITY) return fail(err, "world_wait: a bank was corrupted (internal error)");
+  if (err == MCB200_ERR_TIMEOUT && c.bank_full)
+    return fail(err, "world_wait: the run stopped making progress with a full bank (raise bank_cap)");
   if (err == MCB200_ERR_RANGE) return fail(err, "a particle weight or deposit is outside (-2^7, 2^7)");
   if (err) return fail(err, "world_wait: the kernel reported an error");
   return MCB200_OK;

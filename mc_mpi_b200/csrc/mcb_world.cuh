@@ -86,7 +86,8 @@ struct WorldCounters {
   unsigned long long idle_polls, blocked_passes, bank_pushes, bank_pops;
   unsigned long long lane_slots;     // 32 x event iterations of all warps: events / lane_slots = utilisation
   unsigned long long idle_ns;        // summed over warps: time without a single live history
-  unsigned acc_range, pad;
+  unsigned acc_range;
+  unsigned bank_full;                // a bank had no room for a blocked warp's records (they stayed in the ring)
 };
 
 struct WorldParams {

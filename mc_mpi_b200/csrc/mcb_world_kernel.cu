@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
       // ================================================================== the pass ==
       const bool fin = active && !alive;
       const unsigned fm = __ballot_sync(MCB_FULL, fin);
-      bool blocked = false;
+      unsigned blocked = 0u;   // bit c: the outbound stripe on side c was full
       // a warp without a single live history: the time until it has one again is idle time
       unsigned long long t_idle0 = 0ull;
       if (nolive == MCB_FULL && fm == 0u) t_idle0 = global_timer_ns();
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             if (wr_c[c] + cnt - cred_c[c] > cap)   // full as far as we know: look again
               cred_c[c] = ld_relaxed_sys(sm->win.out[c].credit + wv);
             if (wr_c[c] + cnt - cred_c[c] > cap) {
-              blocked = true;   // ring full: these lanes keep their escapee and retry
+              blocked |= 1u << c;   // ring full: these lanes keep their escapee and retry
             } else {
               if (goes[c]) {
                 // with a neighbour on another GPU these three stores ARE the communication
@@ -486,30 +486,43 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         __syncwarp();
       }
 
-      // (3) blocked senders: make room for the neighbours by moving this warp's inbound
-      // stripes into the CTA's bank -- two windows can then never wait on each other
+      // (3) a blocked sender makes room for THAT neighbour: the records the neighbour sent this
+      // way move from the ring into the CTA's bank, so that two windows can never wait on each
+      // other.  Only that side: the other inbound ring keeps filling, which is the back-pressure
+      // the windows upstream (and the birth pacing of the source) react to.
       if (blocked) {
         __syncwarp();
         if (lane == 0) atomicAdd(&sm->blocked, 1u);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (!(c ? present1 : present0)) continue;
+          if (!((blocked >> c) & 1u) || !(c ? present1 : present0)) continue;
           const unsigned rd = wx->rd[c];
           const unsigned q = rd + (unsigned)lane;
           unsigned long long a, b, d;
           const bool valid = slot_load(sm->win.in[c].rec + ((size_t)wv * cap + (q & (cap - 1u))) * 3,
                                        ((q >> ring_log2) + 1u) & 1u, a, b, d);
           const unsigned rv = __ballot_sync(MCB_FULL, valid);
-          const unsigned take = rv == MCB_FULL ? 32u : (unsigned)(__ffs((int)~rv) - 1);
+          unsigned take = rv == MCB_FULL ? 32u : (unsigned)(__ffs((int)~rv) - 1);
           if (take == 0u) continue;
+          // reserve bank slots; never closer than one claim of every warp (32 x warps) to the
+          // slots a popper may still be reading, never beyond the capacity (what does not fit
+          // stays in the ring)
           unsigned t = 0u;
           if (lane == 0) {
-            t = atomicAdd(&sm->bank_tail, take);
-            if (t + take - *(volatile unsigned *)&sm->bank_head > bank_cap)
-              atomicExch(&p.ctrl->error, (unsigned)(-MCB200_ERR_CAPACITY));
-            atomicAdd(&sm->bank_pushes, take);
+            const unsigned margin = 32u * (unsigned)nwarps;
+            for (;;) {
+              t = *(volatile unsigned *)&sm->bank_tail;
+              const unsigned used = t - *(volatile unsigned *)&sm->bank_head;
+              const unsigned room = used + margin < bank_cap ? bank_cap - margin - used : 0u;
+              if (room < take) take = room;
+              if (take == 0u || atomicCAS(&sm->bank_tail, t, t + take) == t) break;
+            }
+            if (take) atomicAdd(&sm->bank_pushes, take);
+            else atomicExch(&p.ctr->bank_full, 1u);
           }
           t = __shfl_sync(MCB_FULL, t, 0);
+          take = __shfl_sync(MCB_FULL, take, 0);
+          if (take == 0u) continue;
           if ((unsigned)lane < take) {
             unsigned long long s2;
             float x2, mu2, w2;
