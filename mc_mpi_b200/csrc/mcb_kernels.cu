@@ -311,19 +311,23 @@ cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg, cudaStrea
 template <bool TO_BANK>
 __global__ void __launch_bounds__(256) gather_stripes_kernel(
     const unsigned long long *__restrict__ scratch, const unsigned *__restrict__ fills,
-    int nstripes, int stripe_cap, long long ovf_base, unsigned long long *__restrict__ dst_rec,
-    float4 *__restrict__ dst_st, long long dst_n, unsigned long long *out_total) {
+    int nstripes, int stripe_cap, long long ovf_base, long long ovf_cap,
+    unsigned long long *__restrict__ dst_rec, float4 *__restrict__ dst_st, long long dst_n,
+    unsigned long long *out_total) {
   __shared__ unsigned long long s_part[8];
   const int seg = blockIdx.x;
+  // a fill counter is never trusted beyond the segment it counts (a sender with another
+  // geometry, a corrupted table): what is copied always lies inside the stripes
+  const unsigned cap_ovf = ovf_cap < 0xffffffffll ? (unsigned)ovf_cap : 0xffffffffu;
   unsigned long long before = 0ull;
-  for (int t = threadIdx.x; t < seg; t += blockDim.x) before += fills[t];
+  for (int t = threadIdx.x; t < seg; t += blockDim.x) before += min(fills[t], (unsigned)stripe_cap);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(MCB_FULL, before, o);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = before;
   __syncthreads();
   before = 0ull;
   for (int w = 0; w < (int)(blockDim.x >> 5); ++w) before += s_part[w];
-  const unsigned n = fills[seg];
+  const unsigned n = min(fills[seg], seg == nstripes ? cap_ovf : (unsigned)stripe_cap);
   const long long src = seg == nstripes ? ovf_base : (long long)seg * stripe_cap;
   const unsigned long long *from = scratch + 3 * src;
   if (!TO_BANK) {
@@ -343,21 +347,22 @@ __global__ void __launch_bounds__(256) gather_stripes_kernel(
 }
 
 cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsigned *fills,
-                                  int nstripes, int stripe_cap, long long ovf_base,
+                                  int nstripes, int stripe_cap, long long ovf_base, long long ovf_cap,
                                   unsigned long long *settled, long long settled_n,
                                   unsigned long long *out_total, cudaStream_t stream) {
   gather_stripes_kernel<false><<<nstripes + 1, 256, 0, stream>>>(
-      scratch, fills, nstripes, stripe_cap, ovf_base, settled, nullptr, settled_n, out_total);
+      scratch, fills, nstripes, stripe_cap, ovf_base, ovf_cap, settled, nullptr, settled_n, out_total);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gather_stripes_to_bank(const unsigned long long *scratch,
                                           const unsigned *fills, int nstripes, int stripe_cap,
-                                          long long ovf_base, unsigned long long *bank_seed,
-                                          float4 *bank_st, long long bank_n,
-                                          unsigned long long *out_total, cudaStream_t stream) {
+                                          long long ovf_base, long long ovf_cap,
+                                          unsigned long long *bank_seed, float4 *bank_st,
+                                          long long bank_n, unsigned long long *out_total,
+                                          cudaStream_t stream) {
   gather_stripes_kernel<true><<<nstripes + 1, 256, 0, stream>>>(
-      scratch, fills, nstripes, stripe_cap, ovf_base, bank_seed, bank_st, bank_n, out_total);
+      scratch, fills, nstripes, stripe_cap, ovf_base, ovf_cap, bank_seed, bank_st, bank_n, out_total);
   return cudaGetLastError();
 }
 

@@ -106,7 +106,7 @@ cudaError_t launch_track(const TrackParams &p, const TrackLaunch &cfg,
 // pack the stripes (+ overflow segment) of one side behind `settled_n` records of the
 // layer's contiguous outbox; adds the number of records to *out_total
 cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsigned *stripe_n,
-                                  int nstripes, int stripe_cap, long long ovf_base,
+                                  int nstripes, int stripe_cap, long long ovf_base, long long ovf_cap,
                                   unsigned long long *settled, long long settled_n,
                                   unsigned long long *out_total, cudaStream_t stream);
 
@@ -114,9 +114,10 @@ cudaError_t launch_gather_stripes(const unsigned long long *scratch, const unsig
 // into the bank layout behind `bank_n` particles; *out_total = number of particles added
 cudaError_t launch_gather_stripes_to_bank(const unsigned long long *scratch,
                                           const unsigned *fills, int nstripes, int stripe_cap,
-                                          long long ovf_base, unsigned long long *bank_seed,
-                                          float4 *bank_st, long long bank_n,
-                                          unsigned long long *out_total, cudaStream_t stream);
+                                          long long ovf_base, long long ovf_cap,
+                                          unsigned long long *bank_seed, float4 *bank_st,
+                                          long long bank_n, unsigned long long *out_total,
+                                          cudaStream_t stream);
 
 // device-side birth (src/layer.cpp:101-120): particle i of the batch gets
 // seed = rnd_seed^(i+1)(chain_state), mu from the first rnd_real draw

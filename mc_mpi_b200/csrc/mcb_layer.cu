@@ -300,7 +300,14 @@ int track(mcb200_layer *l, long long take) {
     if (l->peer[s].base) {
       // direct peer exchange: the stripes live in the neighbour's inbox, with ITS geometry
       if (grid > l->peer[s].geom.nstripes || take > l->peer[s].geom.max_take)
-        return fail(MCB200_ERR_CAPACITY, "internal: launch does not fit the peer's inbox");
+        return fail(MCB200_ERR_CAPACITY,
+                    "track: this launch (" + std::to_string(grid) + " CTAs, " + std::to_string(take) +
+                        " particles) does not fit the neighbour's inbox (" +
+                        std::to_string(l->peer[s].geom.nstripes) + " stripes, max_take " +
+                        std::to_string(l->peer[s].geom.max_take) +
+                        "): inboxes are sized for the default launch shape (4 CTAs of 256 threads "
+                        "per SM); do not combine \"block\" / \"blocks_per_sm\" options with a "
+                        "connected neighbour");
       continue;
     }
     int rc = rec_reserve(l, &l->d_scratch[s], &l->scratch_cap[s], 0, ovf_base + take);
@@ -357,7 +364,7 @@ int track(mcb200_layer *l, long long take) {
     if (!write_side[s] || l->peer[s].base) continue;  // peer sides: already delivered
     MCB_CUDA(mcb::launch_gather_stripes(l->d_scratch[s],
                                         l->d_stripe_n + s * (mcb::kStripes + 1), grid, stripe_cap,
-                                        ovf_base, l->d_out[s], l->n_out[s],
+                                        ovf_base, take, l->d_out[s], l->n_out[s],
                                         &l->d_ctr->out_total[s], l->stream));
     l->gpu_launches++;
   }
@@ -966,7 +973,7 @@ int mcb200_layer_ingest_inbox(mcb200_layer *l, int32_t from_side, int32_t parity
   MCB_CUDA(cudaMemsetAsync(&l->d_ctr->out_total[0], 0, sizeof(unsigned long long), l->stream));
   MCB_CUDA(mcb::launch_gather_stripes_to_bank(
       reinterpret_cast<const unsigned long long *>(slot), fills, q.nstripes, q.stripe_cap,
-      (long long)q.nstripes * q.stripe_cap, l->bank.seed, l->bank.st, l->n_bank,
+      (long long)q.nstripes * q.stripe_cap, q.ovf_cap, l->bank.seed, l->bank.st, l->n_bank,
       &l->d_ctr->out_total[0], l->stream));
   l->gpu_launches++;
   // the slot is written again two cycles from now: its fill counters must be zero by then

@@ -270,7 +270,8 @@ def split_cells(nb_cells: int, world_size: int, world_rank: int):
 
 def decompose_domain(x_min, x_max, x_ini, world_size, world_rank, nb_cells, nb_particles,
                      particle_min_weight, *, device=0, global_dx=False, keep_border=False,
-                     sigs=None, absorption_rates=None, seed=SEED0, cells=None) -> Layer:
+                     sigs=None, absorption_rates=None, seed=SEED0, cells=None,
+                     left_border=None, right_border=None) -> Layer:
     """decompose_domain, src/layer.cpp:17-42, float arithmetic mirrored in float32.
 
     global_dx=False reproduces the reference (every layer recomputes its own dx
@@ -298,6 +299,7 @@ def decompose_domain(x_min, x_max, x_ini, world_size, world_rank, nb_cells, nb_p
         absorption_rates = a_all if absorption_rates is None else absorption_rates
     layer = Layer(lo, hi, start_index, nb_my_cells, particle_min_weight,
                   device=device, dx=dx if global_dx else None, keep_border=keep_border,
+                  left_border=left_border, right_border=right_border,
                   sigs=None if sigs is None else np.asarray(sigs, dtype=np.float32)[sl],
                   absorption_rates=(None if absorption_rates is None
                                     else np.asarray(absorption_rates, dtype=np.float32)[sl]))

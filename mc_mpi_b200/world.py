@@ -129,7 +129,11 @@ class SlabWorld:
             cfg.x_min, cfg.x_max, cfg.x_ini, self.world_size, self.rank, cfg.nb_cells,
             cfg.nb_particles, cfg.particle_min_weight, device=self.device,
             global_dx=self.global_dx, sigs=cfg.sigs, absorption_rates=cfg.absorption_rates,
-            cells=(lo, hi - lo) if self.global_dx else None)
+            cells=(lo, hi - lo) if self.global_dx else None,
+            # the slab's borders are rank 0's left and the last rank's right edge, whatever the
+            # coordinates: the reference's |x| < 1e-4 heuristic (src/layer.cpp:47-48) would take an
+            # interior cut of a fine grid for a border, and miss a border of a slab not ending at 1
+            left_border=self.rank == 0, right_border=self.rank == self.world_size - 1)
 
     def recut(self, cuts):
         """move the sub-slab boundaries (between runs: the layer is rebuilt, tallies reset)"""

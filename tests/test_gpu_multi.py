@@ -27,6 +27,7 @@ def test_multi_gpu_equals_single_gpu(gpu, mcb_lib, config, n, cuts, transport):
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:]
     assert "tally_bit_exact=True" in res.stdout
+    assert f"transport={transport}" in res.stdout    # no silent fall-back to the other transport
 
 
 @pytest.mark.parametrize("case,cuts,windows", [

@@ -61,11 +61,16 @@ def main():
         print(f"[multi-gpu parity] K={K} config={cfg.name} histories={n} cycles={s['cycles']} "
               f"migrations/history={mig / n:.3f} events={ev} tally_bit_exact={ok}", flush=True)
         one.close()
-        if not ok:
-            dist.destroy_process_group()
-            sys.exit(1)
+        if w.transport != transport:
+            print(f"[multi-gpu parity] asked for transport={transport}, ran {w.transport}", flush=True)
+            ok = False
+    # every rank learns the verdict and closes the world (unmapping peers is collective) before
+    # anybody exits: a failing rank 0 must not leave the others waiting in a barrier
+    flag = torch.tensor([1 if (rank != 0 or ok) else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     w.close()
     dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
 if __name__ == "__main__":
