@@ -224,7 +224,7 @@ WORKLOADS = {
               10_000_000, "optically thick scattering-dominated slab: sigs x1000, a = 0.01 "
                           "(BASELINE configs[3])", "layer"),
     "hetero_1e6": (lambda n: _configs().heterogeneous(1_000_000, n),
-                   100_000, "heterogeneous per-cell cross-sections, 1e6 cells (BASELINE configs[4]); "
+                   2_000_000, "heterogeneous per-cell cross-sections, 1e6 cells (BASELINE configs[4]); "
                             "the slab is cut into shared-memory-sized windows inside the GPU", "world"),
 }
 

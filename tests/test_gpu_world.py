@@ -78,6 +78,8 @@ CASES = {
     "hetero_8192_xs_global": (configs.heterogeneous(8192, 256), 1, dict(xs_global=1)),
     "ranks3_xs_global": (configs.reference_default(20_000), 3, dict(max_ctas=148, xs_global=1)),
     "hetero_20000_ranks2": (configs.heterogeneous(20_000, 200), 2, dict(max_ctas=256)),
+    # BASELINE config 5 at full width: 1e6 heterogeneous cells in ~590 windows of one CTA each
+    "hetero_1e6_windows": (configs.heterogeneous(1_000_000, 64), 1, {}),
 }
 
 
