@@ -262,7 +262,18 @@ def run_culayer_courtesy(args):
                 best = row
         return best
 
+    def run_warm(path):
+        if not os.path.isfile(path):
+            return None
+        r = subprocess.run([path, str(n)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                           timeout=900, cwd=os.path.dirname(path))
+        m = re.search(r"GPU warm = ([0-9.eE+-]+) seconds", r.stdout)
+        return float(m.group(1)) if m else None
+
     a, b = run(ours), run(proto)
+    bin_dir = os.path.join(ROOT, "tests", "dropin", "_bin")
+    warm_ours = run_warm(os.path.join(bin_dir, "culayer_warm_b200"))
+    warm_proto = run_warm(os.path.join(bin_dir, "culayer_warm_proto"))
     if not a or "gpu_s" not in a:
         raise SystemExit(f"bench.py: {ours} is missing or failed ({a}); run __graft_entry__.build()")
     line = {
@@ -275,6 +286,11 @@ def run_culayer_courtesy(args):
                                "(cold: context creation and allocations inside)",
                    "workload_key": "culayer", "histories_per_step": n},
         "cusimulate_ours": a,
+        "warm": {"what": "tests/dropin/culayer_warm.cu: the same configuration, cusimulate() called three "
+                         "times on fresh copies, best of the last two (context, allocations warm)",
+                 "ours_s": warm_ours, "reference_gpu_s": warm_proto,
+                 "ours_histories_per_s": n / warm_ours if warm_ours else None,
+                 "reference_gpu_histories_per_s": n / warm_proto if warm_proto else None},
         "reference_gpu": (dict(b, value=(n / b["gpu_s"] if b and b.get("gpu_s") else None),
                                what="the reference's prototype src/culayer.cu + culayer_kernel.cu, "
                                     "unmodified, nvcc -gencode arch=compute_100a,code=sm_100a "
