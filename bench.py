@@ -621,8 +621,8 @@ def run_world_arm(args, world, rank, dev):
             new = balanced_cuts(cuts, cost, cfg.nb_cells)
             calibration.append({"cuts": cuts, "basis": "events + segments" if it == 0 else "lane occupancy",
                                 "cost_per_rank": [round(c / max(cost), 4) for c in cost]})
-            if new == cuts:
-                break
+            if new == cuts or (it > 0 and min(cost) > 0.97 * max(cost)):
+                break   # balanced within 3 %
             wk.recut(new)
             arm(wk)
             if rank == 0 and args.verbose:
@@ -743,7 +743,7 @@ def main():
                     help="keep the reference's equal-cell-count decomposition")
     ap.add_argument("--seg-cost", type=float, default=25.0, dest="seg_cost",
                     help="N > 1 load model: cost of one history segment in events")
-    ap.add_argument("--calibrations", type=int, default=3,
+    ap.add_argument("--calibrations", type=int, default=5,
                     help="N > 1: load-balancing steps before the warm-up (1 model-based, then "
                          "from the measured lane occupancy)")
     ap.add_argument("--retire-batch", type=int, default=0, dest="retire_batch")

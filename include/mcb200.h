@@ -259,6 +259,7 @@ typedef struct mcb200_world_geom {
   int64_t block_bytes;
   int64_t off_rec[2];        /* rings filled by the left [0] / right [1] neighbour */
   int64_t off_credit[2];     /* credits for this rank's own sends to the left / right */
+  int64_t off_chain;         /* per-stripe counts of disabled histories (used on the home rank) */
 } mcb200_world_geom;
 
 /* one rank's share of a run (counters are for THIS run; the tally is cumulative) */

@@ -82,7 +82,7 @@ class WorldGeom(C.Structure):
     _fields_ = [
         ("rank", C.c_int32), ("world_size", C.c_int32), ("stripes", C.c_int32),
         ("ring_cap", C.c_int32), ("block_bytes", C.c_int64),
-        ("off_rec", C.c_int64 * 2), ("off_credit", C.c_int64 * 2),
+        ("off_rec", C.c_int64 * 2), ("off_credit", C.c_int64 * 2), ("off_chain", C.c_int64),
     ]
 
 

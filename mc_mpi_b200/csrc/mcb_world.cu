@@ -235,6 +235,8 @@ int alloc_device(mcb200_world *w) {
     q.off_credit[s] = (int64_t)off;
     off += cnt_bytes;
   }
+  q.off_chain = (int64_t)off;   // one counter per stripe: histories of that chain disabled anywhere
+  off += cnt_bytes;
   q.block_bytes = (int64_t)off;
   MCB_CUDA(cudaMalloc(&w->d_xblock, off));
   MCB_CUDA(cudaMemsetAsync(w->d_xblock, 0, off, w->stream));
@@ -460,16 +462,18 @@ int mcb200_world_create(const mcb200_world_desc *d, mcb200_world **out) {
                                 (unsigned long long)w->cfg.block;
   // rings: a stripe holds what one chain of warps (stripe s of every window of every rank) can
   // have in flight -- the records pile up in front of the slowest window, and a full ring costs
-  // the sender its lanes -- within [64, 4096] records, at least ~2M records per link
+  // the sender its lanes -- within [64, 8192] records, at least ~2M records per link
   if (d->ring_cap > 0) {
     if (d->ring_cap < 32 || (d->ring_cap & (d->ring_cap - 1)))
       return bail(fail(MCB200_ERR_INVALID, "world_create: ring_cap must be a power of two >= 32"));
     w->ring_cap = (unsigned)d->ring_cap;
   } else {
-    const unsigned chain = pow2_ceil(w->inflight_limit / (unsigned long long)w->S + 1ull);
+    // twice a chain's share of the histories in flight (births are throttled per chain, so a
+    // ring cannot be filled by its own chain: senders practically never lose lanes to a full ring)
+    const unsigned chain = pow2_ceil(2ull * (w->inflight_limit / (unsigned long long)w->S) + 1ull);
     const unsigned bulk = pow2_ceil((2u << 20) / (unsigned)w->S);
     unsigned c = chain > bulk ? chain : bulk;
-    w->ring_cap = c < 64 ? 64 : c > 4096 ? 4096 : c;
+    w->ring_cap = c < 64 ? 64 : c > 8192 ? 8192 : c;
   }
   // banks: 512 MB per rank in total, per CTA a power of two in [1024, 1M] records
   if (d->bank_cap > 0) {
@@ -643,6 +647,13 @@ int mcb200_world_launch(mcb200_world *w) {
   p.ctrl = reinterpret_cast<mcb::WorldCtrl *>(w->d_xblock);
   p.home_disabled =
       &reinterpret_cast<mcb::WorldCtrl *>(w->peers[(size_t)w->home_rank].base)->disabled_global;
+  p.home_chain_disabled = reinterpret_cast<unsigned *>(w->peers[(size_t)w->home_rank].base +
+                                                      w->peers[(size_t)w->home_rank].geom.off_chain);
+  // a chain (stripe s of every window of every rank) gets its share of the histories in flight
+  {
+    const unsigned long long per = w->inflight_limit / (unsigned long long)w->S;
+    p.chain_limit = per < 64ull ? 64u : per > 0x7fffffffull ? 0x7fffffffu : (unsigned)per;
+  }
   p.done_ptrs = w->d_done_ptrs;
   p.n_ranks = w->K;
   p.is_home = is_home ? 1 : 0;

@@ -26,7 +26,12 @@
 //   * termination (StateComm, src/state_comm.cpp:35-65; MPI_Allreduce,
 //     src/worker_sync.cpp:112-120): every CTA adds the histories it disabled to ONE 64-bit
 //     device-side counter on the home rank (system-scope red over NVLink); the home rank's
-//     idle warps compare it with nb_particles and raise every rank's `done` flag.
+//     idle warps compare it with nb_particles and raise every rank's `done` flag;
+//   * flow control: a warp only ever feeds "its" stripe of the neighbouring windows, so stripe s
+//     of every window of every rank forms a CHAIN.  Every warp also reports the histories it
+//     disables to a per-chain counter on the home rank, and a source warp gives birth only
+//     while its own chain holds less than its share of the histories in flight: no chain can
+//     hoard the global budget in the queue of a slow warp while the others run dry.
 #pragma once
 #include "mcb_kernels.cuh"
 
@@ -112,6 +117,10 @@ struct WorldParams {
   unsigned long long total;          // nb_particles of the run
   WorldCtrl *ctrl;                   // this rank's
   unsigned long long *home_disabled; // &home->disabled_global (peer-mapped unless home)
+  unsigned *home_chain_disabled;     // home rank's per-stripe counts of disabled histories [stripes]
+  unsigned chain_limit;              // births of a source warp pause above this many live histories
+                                     // of ITS chain (stripe s of every window of every rank)
+  unsigned pad1;
   unsigned *const *done_ptrs;        // home rank: every rank's &ctrl->done [n_ranks]
   int n_ranks, is_home;
   unsigned long long max_run_ns;     // idle warps end the run (error) after this long; 0 = never

@@ -57,6 +57,9 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 __device__ __forceinline__ void red_add_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_sys(unsigned *p, unsigned v) {
+  asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -73,7 +76,8 @@ struct __align__(16) WarpXchg {
   unsigned backoff;        // iterations to wait after a pass that found nothing (doubles to 16)
   unsigned nap;            // ns an idle warp sleeps between looks (doubles to 2 us)
   unsigned src_done;       // no (more) births to hand out
-  unsigned pad[5];
+  unsigned born;           // histories this warp gave birth to (its chain's intake)
+  unsigned pad[4];
 };
 
 struct WorldSmem {
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             if (lane == 0) {
               atomicAdd(&sm->n_cls[c], cnt);
               note_disabled(sm, p, cnt);
+              red_add_sys(p.home_chain_disabled + wv, cnt);
             }
           } else {
             // stripe `wv` of the neighbouring window: all-or-nothing per warp and side
@@ -296,6 +301,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           if (lane == 0) {
             atomicAdd(&sm->n_cls[2], (unsigned)__popc(md));
             note_disabled(sm, p, (unsigned)__popc(md));
+            red_add_sys(p.home_chain_disabled + wv, (unsigned)__popc(md));
           }
         }
         __syncwarp();
@@ -402,15 +408,38 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
       if (im != 0u && !wx->src_done) {
         // births, src/layer.cpp:101-120: particle i carries rnd_seed^(i+1)(chain_state) and
         // consumes the first draw of its own stream for mu.  Source particles are handed to
-        // warps in chunks of kWorkChunk -- claimed only while the histories in flight
-        // (born - disabled, both counted on this rank) stay below the limit.  Claiming a
-        // chunk computes all its particle seeds at once, lane L those of particles L and
-        // L + 32 (one 63-step jump-ahead per lane and chunk), and parks them in shared memory.
+        // warps in chunks of kWorkChunk.  Claiming a chunk computes all its particle seeds at
+        // once, lane L those of particles L and L + 32 (one 63-step jump-ahead per lane and
+        // chunk), and parks them in shared memory.
         unsigned w_off = wx->w_off, w_cnt = wx->w_cnt;
-        // pacing: no births while one of this warp's outbound stripes is more than half full --
-        // the source follows the rate its neighbours take records at instead of running into a
-        // full ring (which would cost it its lanes) or flooding the banks downstream
-        bool room = true;
+        const unsigned born_chain = wx->born;
+        // Throttle 1: the histories in flight in the whole world (born - disabled, both counted
+        // on this rank).  Throttle 2: the histories in flight of THIS warp's chain -- its own
+        // births minus what every rank reported back for stripe `wv`: a chain never takes more
+        // than its share, so none can hoard the budget in front of a slow warp downstream
+        // while the others run dry.  (A record that changed chains through a bank is credited
+        // to the other chain; if the world as a whole runs low, throttle 2 steps aside.)
+        unsigned long long born_all = 0ull;
+        unsigned live_all_lo = 0u, chain_disabled = 0u;
+        if (lane == 0) {
+          born_all = ld_relaxed_sys(&p.ctrl->born);
+          const unsigned long long live = born_all - ld_relaxed_sys(&p.ctrl->disabled_global);
+          live_all_lo = live > 0xffffffffull ? 0xffffffffu : (unsigned)live;
+          chain_disabled = ld_relaxed_sys(p.home_chain_disabled + wv);
+        }
+        born_all = __shfl_sync(MCB_FULL, born_all, 0);
+        live_all_lo = __shfl_sync(MCB_FULL, live_all_lo, 0);
+        chain_disabled = __shfl_sync(MCB_FULL, chain_disabled, 0);
+        const bool world_full = (unsigned long long)live_all_lo >= p.inflight_limit;
+        const bool world_low = (unsigned long long)live_all_lo < (p.inflight_limit >> 3);
+        const int chain_live = (int)(born_chain - chain_disabled);
+        unsigned allowed = chain_live < (int)p.chain_limit ? p.chain_limit - (unsigned)max(chain_live, 0) : 0u;
+        if (world_low && allowed < 32u) allowed = 32u;
+        // (`born` counts the chunks CLAIMED, so throttle 1 gates the claims only: a warp always
+        // may hand out what it has claimed)
+        // Throttle 3, pacing: no births while one of this warp's outbound stripes is more than
+        // half full -- the source follows the rate its neighbours take records at instead of
+        // running into a full ring (which would cost it its lanes)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if ((c ? mode1 : mode0) == 0) continue;
@@ -420,41 +449,37 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
             cred = ld_relaxed_sys(sm->win.out[c].credit + wv);
             __syncwarp();
             if (lane == 0) wx->cred[c] = cred;
-            if (wr - cred > (cap >> 1)) room = false;
+            if (wr - cred > (cap >> 1)) allowed = 0u;
           }
         }
         __syncwarp();
-        if (w_off == w_cnt && room) {
-          unsigned long long base = ~0ull;
-          if (lane == 0) {
-            const unsigned long long b = ld_relaxed_sys(&p.ctrl->born);
-            if (b >= p.src_total) base = p.src_total;
-            else if (b - ld_relaxed_sys(&p.ctrl->disabled_global) < p.inflight_limit)
-              base = atomicAdd(&p.ctrl->born, (unsigned long long)kWorkChunk);
+        if (w_off == w_cnt && ((allowed != 0u && !world_full) || born_all >= p.src_total)) {
+          unsigned long long base = p.src_total;
+          if (born_all < p.src_total) {
+            if (lane == 0) base = atomicAdd(&p.ctrl->born, (unsigned long long)kWorkChunk);
+            base = __shfl_sync(MCB_FULL, base, 0);
           }
-          base = __shfl_sync(MCB_FULL, base, 0);
-          if (base != ~0ull) {
-            if (base >= p.src_total) {
-              if (lane == 0) wx->src_done = 1u;
+          if (base >= p.src_total) {
+            if (lane == 0) wx->src_done = 1u;
+          } else {
+            if (RNG == 0) {
+              const unsigned long long s = jump_state(c_seed_jump, base + 1ull + (unsigned)lane,
+                                                      p.chain_state);
+              s_birth[lane] = lcg_next(s);                                   // :112 draw #1
+              s_birth[lane + 32] = lcg_next(affine_apply(c_seed_jump.pow2[5], s));
             } else {
-              if (RNG == 0) {
-                const unsigned long long s = jump_state(c_seed_jump, base + 1ull + (unsigned)lane,
-                                                        p.chain_state);
-                s_birth[lane] = lcg_next(s);                                   // :112 draw #1
-                s_birth[lane + 32] = lcg_next(affine_apply(c_seed_jump.pow2[5], s));
-              } else {
-                // counter-based: history `base + j` is its own counter, event 0 = the birth
-                s_birth[lane] = (base + (unsigned)lane) << kPhiloxEventBits;
-                s_birth[lane + 32] = (base + 32ull + (unsigned)lane) << kPhiloxEventBits;
-              }
-              __syncwarp();
-              w_off = 0u;
-              w_cnt = base + kWorkChunk <= p.src_total ? (unsigned)kWorkChunk
-                                                       : (unsigned)(p.src_total - base);
+              // counter-based: history `base + j` is its own counter, event 0 = the birth
+              s_birth[lane] = (base + (unsigned)lane) << kPhiloxEventBits;
+              s_birth[lane + 32] = (base + 32ull + (unsigned)lane) << kPhiloxEventBits;
             }
+            __syncwarp();
+            w_off = 0u;
+            w_cnt = base + kWorkChunk <= p.src_total ? (unsigned)kWorkChunk
+                                                     : (unsigned)(p.src_total - base);
           }
         }
-        const unsigned avail = room ? w_cnt - w_off : 0u;
+        unsigned avail = w_cnt - w_off;
+        if (avail > allowed) avail = allowed;
         const unsigned nidle = (unsigned)__popc(im);
         const unsigned n = avail < nidle ? avail : nidle;
         if (n) {
@@ -468,7 +493,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
               seed += 1ull;
             }
             rmu = recip_for_div(mu);
-          step = dir_step(mu);
+            step = dir_step(mu);
             x = p.x_ini;
             wmc = p.wmc;
             idx = p.src_index;
@@ -482,6 +507,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         if (lane == 0) {
           wx->w_off = w_off;
           wx->w_cnt = w_cnt;
+          wx->born = born_chain + n;
         }
         __syncwarp();
       }
