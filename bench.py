@@ -608,27 +608,43 @@ def run_world_arm(args, world, rank, dev):
     if args.balance:
         # measured load balancing: the result does not depend on the cuts (one global dx, one
         # global cross-section table: bit for bit), so they go where the measured work balances.
-        # First step from the work model (events + segments), then from the measured occupancy
-        # of the lanes (a rank whose lanes wait for its neighbours gets more cells).
-        res = eq_res[-1]
+        # First step from the work model (events + segments), then damped steps from the measured
+        # occupancy of the lanes (a rank whose lanes wait for its neighbours gets more cells);
+        # every candidate is timed on a whole step and the fastest one is kept.
+        equal_cuts = [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world) for k in range(world + 1)]
+        res, cuts = eq_res[-1], equal_cuts
+        best_ms, best_cuts = eq_ms, equal_cuts
         for it in range(args.calibrations):
             if it == 0:
                 cost = [row[0] for row in wk.all_ranks([rank_cost(res)], "table")]
+                new = balanced_cuts(cuts, cost, cfg.nb_cells)
             else:
                 cost = occupancies(res)
-            cuts = wk.cuts or [k * (cfg.nb_cells // world) + min(k, cfg.nb_cells % world)
-                               for k in range(world + 1)]
-            new = balanced_cuts(cuts, cost, cfg.nb_cells)
-            calibration.append({"cuts": cuts, "basis": "events + segments" if it == 0 else "lane occupancy",
-                                "cost_per_rank": [round(c / max(cost), 4) for c in cost]})
-            if new == cuts or (it > 0 and min(cost) > 0.97 * max(cost)):
-                break   # balanced within 3 %
+                if min(cost) > 0.97 * max(cost):
+                    break   # balanced within 3 %
+                target = balanced_cuts(cuts, cost, cfg.nb_cells)
+                new = [int(round(0.5 * (a + b))) for a, b in zip(cuts, target)]   # damped
+            if new == cuts:
+                break
             wk.recut(new)
             arm(wk)
+            res = wk.spin(n_hist)
+            ms = wk.all_ranks([res["kernel_ms"]], "max")[0]
+            calibration.append({"basis": "events + segments" if it == 0 else "lane occupancy (damped)",
+                                "cost_per_rank": [round(c / max(cost), 4) for c in cost],
+                                "cuts": new, "step_ms": round(ms, 2)})
             if rank == 0 and args.verbose:
-                sys.stderr.write(f"[bench] calibration {it}: cost {calibration[-1]['cost_per_rank']} -> cuts {new}\n")
-            if it + 1 < args.calibrations:
-                res = wk.spin(n_hist)
+                sys.stderr.write(f"[bench] calibration {it}: cost {calibration[-1]['cost_per_rank']} -> "
+                                 f"cuts {new}: {ms:.1f} ms\n")
+            cuts = new
+            if ms < best_ms:
+                best_ms, best_cuts = ms, new
+        if cuts != best_cuts:
+            if best_cuts == equal_cuts:
+                wk.recut(None)
+            else:
+                wk.recut(best_cuts)
+            arm(wk)
     for _ in range(args.warmup):
         wk.spin(n_hist)
     sampler = ClockSampler(dev)
@@ -743,7 +759,7 @@ def main():
                     help="keep the reference's equal-cell-count decomposition")
     ap.add_argument("--seg-cost", type=float, default=25.0, dest="seg_cost",
                     help="N > 1 load model: cost of one history segment in events")
-    ap.add_argument("--calibrations", type=int, default=5,
+    ap.add_argument("--calibrations", type=int, default=4,
                     help="N > 1: load-balancing steps before the warm-up (1 model-based, then "
                          "from the measured lane occupancy)")
     ap.add_argument("--retire-batch", type=int, default=0, dest="retire_batch")

@@ -268,7 +268,7 @@ class Worker:
             self.r.disconnect()
             self._dist.barrier(group=self.group)   # nobody frees a block a peer still maps
         self.r.close()
-        self.cuts = list(cuts)
+        self.cuts = list(cuts) if cuts is not None else None
         self.r = _Rank(self.cfg, self.rank, self.world_size, self.device, self.cuts,
                        **dict(self._opts))
         self._connect()
