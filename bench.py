@@ -628,7 +628,14 @@ def run_world_arm(args, world, rank, dev):
                 break
             wk.recut(new)
             arm(wk)
-            res = wk.spin(n_hist)
+            try:
+                res = wk.spin(n_hist)
+            except _abi.McbError as ex:
+                # a candidate that does not run (every rank sees the same stalled counters and
+                # raises) is dropped, not fatal: back to the best cuts seen so far
+                calibration.append({"cuts": new, "failed": str(ex)[:200]})
+                cuts = None
+                break
             ms = wk.all_ranks([res["kernel_ms"]], "max")[0]
             calibration.append({"basis": "events + segments" if it == 0 else "lane occupancy (damped)",
                                 "cost_per_rank": [round(c / max(cost), 4) for c in cost],
