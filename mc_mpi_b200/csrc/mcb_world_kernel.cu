@@ -214,10 +214,15 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   WarpXchg *wx = &sm->wx[warp];
   // what this warp's stripes look like (warp-uniform; the compiler keeps what fits in uniform
   // registers and re-reads the rest from shared memory)
-  const int mode0 = sm->win.out[0].mode, mode1 = sm->win.out[1].mode;
-  const int present0 = sm->win.in[0].present, present1 = sm->win.in[1].present;
-  const unsigned bank_cap = sm->win.bank.cap, bank_log2 = sm->win.bank.log2cap;
-  unsigned long long *const bank_rec = sm->win.bank.rec + (size_t)cw * bank_cap * 3;
+  // (what only the pass needs -- link modes, bank geometry -- is re-read from shared memory
+  // there, so that it does not occupy registers across the event loop)
+#define mode0 (sm->win.out[0].mode)
+#define mode1 (sm->win.out[1].mode)
+#define present0 (sm->win.in[0].present)
+#define present1 (sm->win.in[1].present)
+#define bank_cap (sm->win.bank.cap)
+#define bank_log2 (sm->win.bank.log2cap)
+#define bank_rec (sm->win.bank.rec + (size_t)cw * sm->win.bank.cap * 3)
 
   // particle state, include/types/particle.hpp:7-18, one history per lane
   unsigned long long seed = 0;
@@ -693,6 +698,14 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     if (owe) red_add_sys(p.home_disabled, (unsigned long long)owe);
   }
 }
+
+#undef mode0
+#undef mode1
+#undef present0
+#undef present1
+#undef bank_cap
+#undef bank_log2
+#undef bank_rec
 
 size_t world_smem_bytes(int m_max, int block, bool xs_smem) {
   return sizeof(WorldSmem) + (size_t)(block / 32) * kWorkChunk * sizeof(unsigned long long) +
