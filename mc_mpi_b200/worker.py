@@ -243,6 +243,10 @@ class Worker:
 
     @property
     def tdev(self):
+        # where the few plumbing tensors (IPC handles, counters) live for the collectives; the
+        # CPU is only ever used by the gloo tests of this host logic (no compute happens here)
+        if not self._torch.cuda.is_available():
+            return self._torch.device("cpu")
         return self._torch.device("cuda", self.device)
 
     def _connect(self):
