@@ -63,3 +63,27 @@ def test_reference_test_layer_perf_on_our_layer(gpu, tmp_path):
     gold = np.loadtxt(os.path.join(GOLD, "WA_1000_1000000.out"))
     rel = np.abs(wa[:, 1] - gold[:, 1]) / gold[:, 1]
     assert wa.shape == (1000, 2) and rel.max() < 2e-3   # 3 significant digits in WA.out
+
+
+def test_whole_run_from_plain_c(gpu, tmp_path):
+    """tests/dropin/world_native.c: K ranks created, connected, run (Worker::spin) and gathered
+    (Worker::gather_weights_absorbed) from C99 through include/mcb200.h only -- no Python, no
+    torch on the path.  Its output equals the single-layer oracle: counts exact, tally equal to
+    the exact sums rounded once."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from mc_mpi_b200 import configs
+    from util import make_oracle
+    exe = _need("world_native")
+    n = 30_000
+    res = subprocess.run([exe, "3", str(n)], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.split("\n")
+    counts = tuple(int(v) for v in lines[0].split())
+    tally = np.array([float(v) for v in lines[1:1001]])
+    o = make_oracle(configs.reference_default(n))
+    o.simulate(-1, nthread=os.cpu_count() or 1)
+    st = o.stats()
+    assert counts == (st["events"], st["scatters"], st["n_left"], st["n_right"], st["n_dead"])
+    assert np.array_equal(tally, o.tally_exact_f64)
