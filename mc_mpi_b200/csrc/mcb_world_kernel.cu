@@ -87,7 +87,7 @@ struct WorldSmem {
   unsigned pend;                // disabled histories not yet added to the home counter
   unsigned births, idle_polls, blocked, bank_pushes, bank_pops;
   unsigned bank_head, bank_tail;   // this CTA's bank: next to pop / next to push
-  unsigned pad;
+  unsigned acc_range;              // a deposit did not fit the accumulator (copied out at exit)
   unsigned long long t_start;   // globaltimer at kernel start (for the run-time cap)
   unsigned long long idle_ns;   // time its warps spent without a single live history
   WarpXchg wx[kWorldMaxWarps];
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
   if (threadIdx.x == 0) {
     sm->t_start = global_timer_ns();
     sm->idle_ns = 0ull;
+    sm->acc_range = 0u;
   }
   if (threadIdx.x < kWorldMaxWarps) {
     WarpXchg z{};
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
           if ((c ? mode1 : mode0) == 0) {
             // global border: absorbed and counted as disabled, src/layer.cpp:350-360
             if (goes[c]) {
-              acc_add_smem(acc_s + (unsigned)(m + c) * 4u, acc_stride, wmc, &p.ctr->acc_range);
+              acc_add_smem(acc_s + (unsigned)(m + c) * 4u, acc_stride, wmc, &sm->acc_range);
               active = false;
             }
             if (lane == 0) {
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
         }
         if (md) {
           if (fin && !goes[0] && !goes[1]) {
-            acc_add_smem(acc_s + (unsigned)(m + 2) * 4u, acc_stride, wmc, &p.ctr->acc_range);
+            acc_add_smem(acc_s + (unsigned)(m + 2) * 4u, acc_stride, wmc, &sm->acc_range);
             active = false;
           }
           if (lane == 0) {
@@ -620,13 +621,13 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     // ---- one event per live lane: Layer::particle_step, src/layer.cpp:123-190
     if (alive) {
       event_step<XS_SMEM, true, RNG>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
-                                acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range, p.rng_key);
+                                acc_stride, gxs, nullptr, ncell, &sm->acc_range, p.rng_key);
       ++n_ev;
       // a second event under the same vote for the lanes that are still live: the loop top is
       // shared by two events; a lane that finished on the first one waits one slot longer
       if ((wmc >= minw) && ((unsigned)(idx - lo) < (unsigned)m)) {
         event_step<XS_SMEM, true, RNG>(seed, x, mu, wmc, rmu, step, idx, n_sc, lo, dx, tb_s, xs_s, acc_s,
-                                  acc_stride, gxs, nullptr, ncell, &p.ctr->acc_range, p.rng_key);
+                                  acc_stride, gxs, nullptr, ncell, &sm->acc_range, p.rng_key);
         ++n_ev;
       }
     }
@@ -690,6 +691,7 @@ __global__ void __launch_bounds__(MAXB, MAXB <= 256 ? 4 : 1) world_kernel(const 
     if (sm->blocked) atomicAdd(&g->blocked_passes, (unsigned long long)sm->blocked);
     if (sm->bank_pushes) atomicAdd(&g->bank_pushes, (unsigned long long)sm->bank_pushes);
     if (sm->bank_pops) atomicAdd(&g->bank_pops, (unsigned long long)sm->bank_pops);
+    if (sm->acc_range) atomicExch(&g->acc_range, 1u);
     // the bank's cursors for the next run (head == tail unless the run was stopped)
     sm->win.bank.ht[2 * cw] = sm->bank_head;
     sm->win.bank.ht[2 * cw + 1] = sm->bank_tail;
