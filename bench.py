@@ -513,6 +513,21 @@ def run_single_arm(args, dev):
     print(json.dumps(line), flush=True)
 
 
+def nvlink_summary(sent_left, sent_right, steps, step_ms):
+    """NVLink traffic of the exchange, from the device counters: every record a rank sends to a
+    neighbour is 24 bytes stored into that neighbour's memory (the credits coming back are 4 bytes
+    per retire / refill pass and are not counted).  ncu's nvltx / nvlrx counters are not readable
+    on this pool, so this is the number the JSON line carries."""
+    rec = [float(a) + float(b) for a, b in zip(sent_left, sent_right)]
+    per_dir = [float(v) for v in list(sent_left) + list(sent_right)]
+    sec = max(steps * step_ms * 1e-3, 1e-12)
+    return {"records_per_step": sum(rec) / max(steps, 1),
+            "bytes_per_step": 24.0 * sum(rec) / max(steps, 1),
+            "busiest_link_direction_GB_per_s": 24.0 * max(per_dir + [0.0]) / sec / 1e9,
+            "note": "24-byte wire records stored by the tracking kernel into the neighbour GPU's "
+                    "rings; NVLink 5 peer copy on this pool: ~770 GB/s per direction"}
+
+
 def run_world_arm(args, world, rank, dev):
     """N > 1: one process per GPU, one sub-slab per GPU, ONE resident kernel per GPU and step
     (mcb200_world_*): escapees are stored straight into the neighbour GPU's memory over NVLink,
@@ -690,6 +705,7 @@ def run_world_arm(args, world, rank, dev):
         "bank_pushes_per_rank": per["bank_pushes"],
         "migrations_per_history": (sum(per["sent_left"]) + sum(per["sent_right"])) / (n_hist * args.steps),
         "ctas": per["ctas"][0], "stripes": per["stripes"][0], "ring_cap": per["ring_cap"][0],
+        "nvlink": nvlink_summary(per["sent_left"], per["sent_right"], args.steps, dev_ms / args.steps),
         "cuts": wk.cuts or "equal", "balanced": bool(args.balance), "calibration": calibration,
         "host_collectives_per_step": "1 barrier in front of the launches; none while the kernels run",
     }

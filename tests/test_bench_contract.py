@@ -47,3 +47,13 @@ def test_gpu_arm_without_a_gpu_fails_loudly(mcb_lib):
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_nvlink_summary_counts_24_bytes_per_record():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.nvlink_summary([0, 100, 200], [300, 400, 0], steps=2, step_ms=1.0)
+    assert s["records_per_step"] == 500 and s["bytes_per_step"] == 12000
+    assert abs(s["busiest_link_direction_GB_per_s"] - 24 * 400 / 2e-3 / 1e9) < 1e-12
