@@ -528,6 +528,23 @@ def nvlink_summary(sent_left, sent_right, steps, step_ms):
                     "rings; NVLink 5 peer copy on this pool: ~770 GB/s per direction"}
 
 
+def settle_fast_regime(step_ms, rebuild, best_ms, tries=3, tolerance=1.05):
+    """The 8-GPU step time of a freshly built world is bimodal (the same cuts
+    measured 346 ms in one job and 404 ms in the next).  `step_ms()` runs one whole step and
+    returns its device time (max over ranks, identical on every rank), `rebuild()` builds the world
+    again with the same cuts (new exchange buffers, new kernels).  Rebuild until a step runs within
+    `tolerance` of the best candidate the calibration saw, at most `tries` times; returns the
+    step times observed."""
+    seen = []
+    for attempt in range(tries + 1):
+        ms = step_ms()
+        seen.append(round(ms, 2))
+        if ms <= tolerance * best_ms or attempt == tries:
+            break
+        rebuild()
+    return seen
+
+
 def run_world_arm(args, world, rank, dev):
     """N > 1: one process per GPU, one sub-slab per GPU, ONE resident kernel per GPU and step
     (mcb200_world_*): escapees are stored straight into the neighbour GPU's memory over NVLink,
@@ -667,6 +684,18 @@ def run_world_arm(args, world, rank, dev):
             else:
                 wk.recut(best_cuts)
             arm(wk)
+
+        def one_step_ms():
+            return wk.all_ranks([wk.spin(n_hist)["kernel_ms"]], "max")[0]
+
+        def rebuild():
+            wk.recut(wk.cuts)
+            arm(wk)
+
+        settle = settle_fast_regime(one_step_ms, rebuild, best_ms)
+        calibration.append({"settle_step_ms": settle, "best_candidate_ms": round(best_ms, 2),
+                            "what": "steps of the world built on the chosen cuts; rebuilt (same cuts) "
+                                    "while slower than 1.05 x the best candidate, at most 3 times"})
     for _ in range(args.warmup):
         wk.spin(n_hist)
     sampler = ClockSampler(dev)

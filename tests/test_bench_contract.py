@@ -57,3 +57,19 @@ def test_nvlink_summary_counts_24_bytes_per_record():
     s = bench.nvlink_summary([0, 100, 200], [300, 400, 0], steps=2, step_ms=1.0)
     assert s["records_per_step"] == 500 and s["bytes_per_step"] == 12000
     assert abs(s["busiest_link_direction_GB_per_s"] - 24 * 400 / 2e-3 / 1e9) < 1e-12
+
+
+def test_settle_fast_regime_rebuilds_until_fast_or_gives_up():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    times, rebuilds = iter([404.0, 398.0, 341.0, 999.0]), []
+    seen = bench.settle_fast_regime(lambda: next(times), lambda: rebuilds.append(1), best_ms=337.0)
+    assert seen == [404.0, 398.0, 341.0] and len(rebuilds) == 2        # third build is fast
+    times, rebuilds = iter([400.0] * 10), []
+    seen = bench.settle_fast_regime(lambda: next(times), lambda: rebuilds.append(1), best_ms=337.0)
+    assert seen == [400.0] * 4 and len(rebuilds) == 3                  # gives up after 3 rebuilds
+    times, rebuilds = iter([330.0]), []
+    assert bench.settle_fast_regime(lambda: next(times), lambda: rebuilds.append(1), 337.0) == [330.0]
+    assert rebuilds == []
